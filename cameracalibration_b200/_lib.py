@@ -1,0 +1,170 @@
+"""ctypes binding of libbevk.so (include/bevk.h).  There is no CPU fallback: if the
+shared library is missing or no CUDA device is present, the calls raise."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbevk.so")
+
+INTER_NEAREST, INTER_LINEAR = 0, 1
+MAPS_UNDISTORT, MAPS_BEV = 0, 1
+MODEL_FISHEYE, MODEL_PINHOLE = 0, 1
+FLAG_BALANCE = 1
+MAX_CAMERAS = 8
+
+_p = C.c_void_p
+_dp = C.POINTER(C.c_double)
+# name -> (restype, argtypes); mirrors include/bevk.h one to one
+SIGNATURES = {
+    "bevk_version": (C.c_int, []),
+    "bevk_last_error": (C.c_char_p, []),
+    "bevk_ctx_create": (C.c_int, [C.c_int, C.POINTER(_p)]),
+    "bevk_ctx_destroy": (C.c_int, [_p]),
+    "bevk_ctx_set_stream": (C.c_int, [_p, _p]),
+    "bevk_ctx_sync": (C.c_int, [_p]),
+    "bevk_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(_p)]),
+    "bevk_host_free": (C.c_int, [_p]),
+    "bevk_undistort_map": (C.c_int, [_p, C.c_int, _dp, _dp, C.c_int, _dp, C.c_int, C.c_int, _p, _p]),
+    "bevk_remap": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int64, C.c_int, _p, _p, C.c_int, C.c_int, _p, C.c_int64, C.c_int]),
+    "bevk_undistorter_set": (C.c_int, [_p, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int]),
+    "bevk_undistorter_maps": (C.c_int, [_p, C.c_int, _p, _p]),
+    "bevk_undistort": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_int, C.c_int64, C.c_int, _p, C.c_int64, C.c_int]),
+    "bevk_warp_perspective": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int64, C.c_int, _dp, _p, C.c_int, C.c_int, C.c_int64, C.c_int]),
+    "bevk_warp_maps": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, _dp, C.c_int, C.c_int, _p, _p]),
+    "bevk_bev_configure": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "bevk_bev_set_camera": (C.c_int, [_p, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, _dp]),
+    "bevk_bev_set_maps": (C.c_int, [_p, C.c_int, _p, _p]),
+    "bevk_bev_get_maps": (C.c_int, [_p, C.c_int, _p, _p]),
+    "bevk_bev_set_mask": (C.c_int, [_p, C.c_int, _p]),
+    "bevk_blend_masks": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, _p]),
+    "bevk_bev_finalize": (C.c_int, [_p]),
+    "bevk_bev_run": (C.c_int, [_p, C.POINTER(_p), C.c_int64, C.c_int, _p, C.c_int, _p]),
+    "bevk_bev_run_device": (C.c_int, [_p, _p, C.c_int, _p, C.c_int, _p]),
+    "bevk_bev_run_device_cams": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _p]),
+    "bevk_sat_sum_device": (C.c_int, [_p, C.POINTER(_p), C.c_int, C.c_uint64, _p, _p]),
+    "bevk_apply_mask": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, _p]),
+    "bevk_color_balance": (C.c_int, [_p, _p, C.c_int, C.c_int, _p]),
+    "bevk_luminance_balance": (C.c_int, [_p, C.POINTER(_p), C.c_int, C.c_int, C.c_int, C.POINTER(_p)]),
+    "bevk_bev_plan_info": (C.c_int, [_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "bevk_launch_count": (C.c_int64, [_p]),
+    "bevk_last_kernel_ms": (C.c_int, [_p, C.POINTER(C.c_float)]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen libbevk.so and type every export.  Raises if the library was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m cameracalibration_b200.build` "
+                "(nvcc, sm_100a).  cameracalibration_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+class BevkError(Exception):
+    pass
+
+
+def check(rc: int):
+    if rc != 0:
+        raise BevkError(f"libbevk error {rc}: {load().bevk_last_error().decode()}")
+
+
+def dptr(a) -> _dp:
+    """float64 C-contiguous view -> double*; keeps the array alive via the returned object."""
+    arr = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
+    p = arr.ctypes.data_as(_dp)
+    p._keep = arr
+    return p
+
+
+def vptr(a: np.ndarray) -> _p:
+    return C.c_void_p(a.ctypes.data)
+
+
+def image_view(img: np.ndarray):
+    """(array to pass, w, h, row stride, channels) for a uint8 HxW or HxWxC image.  Rows
+    must be internally contiguous; otherwise a contiguous copy is made."""
+    if img.dtype != np.uint8:
+        raise BevkError("images must be uint8")
+    if img.ndim == 2:
+        ch = 1
+    elif img.ndim == 3 and img.shape[2] in (1, 3, 4):
+        ch = img.shape[2]
+    else:
+        raise BevkError(f"unsupported image shape {img.shape}")
+    h, w = img.shape[:2]
+    ok = img.strides[1] == ch and (img.ndim == 2 or img.strides[2] == 1) and img.strides[0] >= w * ch
+    if not ok:
+        img = np.ascontiguousarray(img)
+    return img, w, h, img.strides[0], ch
+
+
+class Context:
+    """Owner of a bevk_ctx (one per thread)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = _p()
+        check(self.lib.bevk_ctx_create(int(device), C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bevk_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream_ptr: int | None):
+        check(self.lib.bevk_ctx_set_stream(self.h, _p(stream_ptr or 0)))
+
+    def sync(self):
+        check(self.lib.bevk_ctx_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.bevk_launch_count(self.h))
+
+
+_default_ctx: dict[int, Context] = {}
+
+
+def default_context(device: int | None = None) -> Context:
+    if device is None:
+        device = int(os.environ.get("BEVK_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
+    """numpy array backed by page-locked host memory (full-rate PCIe copies)."""
+    lib = load()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = _p()
+    check(lib.bevk_host_alloc(n, C.byref(p)))
+    buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _pinned_keep[arr.ctypes.data] = (buf, p)
+    return arr
+
+
+_pinned_keep: dict = {}

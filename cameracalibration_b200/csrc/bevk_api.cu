@@ -1,0 +1,811 @@
+// bevk_api.cu -- C ABI of libbevk.so (see include/bevk.h) over the sm_100a kernels.
+// Host side: argument checks, 3x3 inverses the way OpenCV computes them, device
+// buffer management, the tile-plan compiler, stream ordering.  No CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/bevk.h"
+#include "bevk_kernels.cuh"
+
+using namespace bevk;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(e_ == cudaErrorMemoryAllocation ? BEVK_ERR_OOM : BEVK_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);                                     \
+  } while (0)
+#define RET(call)             \
+  do {                        \
+    int r_ = (call);          \
+    if (r_ != BEVK_OK) return r_; \
+  } while (0)
+
+// ------------------------------------------------------------------ small helpers
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return BEVK_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    n = (n + 255) & ~size_t(255);
+    CU(cudaMalloc(&p, n + 256));   // 256 B of slack: the kernels' 32-bit tap loads may touch 3 bytes past a frame
+    cap = n;
+    return BEVK_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// OpenCV's closed-form 3x3 inverse (cv::invert, DECOMP_LU, n == 3, CV_64F).
+static bool inv3(const double* S, double* T) {
+#define M(r, c) S[(r) * 3 + (c)]
+  double d = M(0, 0) * (M(1, 1) * M(2, 2) - M(1, 2) * M(2, 1)) - M(0, 1) * (M(1, 0) * M(2, 2) - M(1, 2) * M(2, 0)) +
+             M(0, 2) * (M(1, 0) * M(2, 1) - M(1, 1) * M(2, 0));
+  if (d == 0.) return false;
+  d = 1. / d;
+  T[0] = (M(1, 1) * M(2, 2) - M(1, 2) * M(2, 1)) * d;
+  T[1] = (M(0, 2) * M(2, 1) - M(0, 1) * M(2, 2)) * d;
+  T[2] = (M(0, 1) * M(1, 2) - M(0, 2) * M(1, 1)) * d;
+  T[3] = (M(1, 2) * M(2, 0) - M(1, 0) * M(2, 2)) * d;
+  T[4] = (M(0, 0) * M(2, 2) - M(0, 2) * M(2, 0)) * d;
+  T[5] = (M(0, 2) * M(1, 0) - M(0, 0) * M(1, 2)) * d;
+  T[6] = (M(1, 0) * M(2, 1) - M(1, 1) * M(2, 0)) * d;
+  T[7] = (M(0, 1) * M(2, 0) - M(0, 0) * M(2, 1)) * d;
+  T[8] = (M(0, 0) * M(1, 1) - M(0, 1) * M(1, 0)) * d;
+#undef M
+  return true;
+}
+
+static int make_model(int model, const double* K, const double* D, int n_dist, const double* P, int w, int h,
+                      CamModel* cm) {
+  if (!K || !P || (n_dist > 0 && !D)) return fail(BEVK_ERR_ARG, "null K/D/P");
+  if (model != BEVK_MODEL_FISHEYE && model != BEVK_MODEL_PINHOLE) return fail(BEVK_ERR_ARG, "bad camera model %d", model);
+  if (w <= 0 || h <= 0) return fail(BEVK_ERR_ARG, "bad map size %dx%d", w, h);
+  memset(cm, 0, sizeof *cm);
+  if (!inv3(P, cm->iR)) return fail(BEVK_ERR_ARG, "P is singular");
+  const int want = model == BEVK_MODEL_FISHEYE ? 4 : 5;
+  for (int i = 0; i < want && i < n_dist; ++i) cm->k[i] = D[i];
+  cm->fx = K[0]; cm->fy = K[4]; cm->cx = K[2]; cm->cy = K[5];
+  cm->model = model; cm->w = w; cm->h = h;
+  return BEVK_OK;
+}
+
+static int make_homog(const double* H, Homog* hm) {
+  if (!H) return fail(BEVK_ERR_ARG, "null H");
+  if (!inv3(H, hm->M)) memset(hm->M, 0, sizeof hm->M);   // cv::invert leaves zeros for a singular matrix
+  return BEVK_OK;
+}
+
+static dim3 grid2d(int w, int h) { return dim3((w + 31) / 32, (h + 7) / 8); }
+
+// ------------------------------------------------------------------ context
+struct Undistorter {
+  bool valid = false, fused = false;
+  CamModel cm;
+  DevBuf map1, map2;
+};
+
+struct BevCam {
+  bool has_maps = false, has_mask = false;
+  DevBuf map1, map2;              // device BEV maps
+  std::vector<uint8_t> mask;      // host mask
+};
+
+struct bevk_ctx {
+  int device = 0;
+  cudaStream_t own = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  long long launches = 0;
+  DevBuf s_src, s_dst, s_m1, s_m2, s_o1, s_o2;   // scratch for the host-pointer entry points
+  Undistorter und[8];
+  // BEV engine
+  int n_cam = 0, FW = 0, FH = 0, BW = 0, BH = 0;
+  BevCam cam[BEVK_MAX_CAMERAS];
+  bool planned = false;
+  long long n_tiles = 0, n_items = 0;
+  DevBuf d_tiles, d_items, d_lut, d_hsv;
+  DevBuf d_frames, d_ptrs, d_canvas, d_car, d_vsum, d_delta, d_csum;
+};
+
+static int use(bevk_ctx* c) {
+  if (!c) return fail(BEVK_ERR_ARG, "null ctx");
+  CU(cudaSetDevice(c->device));
+  return BEVK_OK;
+}
+#define LAUNCHED(c)                 \
+  do {                              \
+    (c)->launches++;                \
+    CU(cudaGetLastError());         \
+  } while (0)
+
+// All bevk_* functions get C linkage from their declarations in include/bevk.h.
+
+int bevk_version(void) { return 100; }
+const char* bevk_last_error(void) { return g_err.c_str(); }
+
+int bevk_ctx_create(int device, bevk_ctx** out) {
+  if (!out) return fail(BEVK_ERR_ARG, "null out");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(BEVK_ERR_CUDA, "no CUDA device (%s); libbevk has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(BEVK_ERR_ARG, "device %d out of range [0,%d)", device, n);
+  CU(cudaSetDevice(device));
+  bevk_ctx* c = new (std::nothrow) bevk_ctx;
+  if (!c) return fail(BEVK_ERR_OOM, "host allocation failed");
+  c->device = device;
+  CU(cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking));
+  c->stream = c->own;
+  CU(cudaEventCreate(&c->ev0));
+  CU(cudaEventCreate(&c->ev1));
+  *out = c;
+  return BEVK_OK;
+}
+
+int bevk_ctx_destroy(bevk_ctx* c) {
+  if (!c) return BEVK_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (DevBuf* b : {&c->s_src, &c->s_dst, &c->s_m1, &c->s_m2, &c->s_o1, &c->s_o2, &c->d_tiles, &c->d_items, &c->d_lut,
+                    &c->d_hsv, &c->d_frames, &c->d_ptrs, &c->d_canvas, &c->d_car, &c->d_vsum, &c->d_delta, &c->d_csum})
+    b->release();
+  for (auto& u : c->und) { u.map1.release(); u.map2.release(); }
+  for (auto& k : c->cam) { k.map1.release(); k.map2.release(); }
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->own);
+  delete c;
+  return BEVK_OK;
+}
+
+int bevk_ctx_set_stream(bevk_ctx* c, void* s) {
+  RET(use(c));
+  c->stream = s ? reinterpret_cast<cudaStream_t>(s) : c->own;
+  return BEVK_OK;
+}
+
+int bevk_ctx_sync(bevk_ctx* c) {
+  RET(use(c));
+  CU(cudaStreamSynchronize(c->stream));
+  return BEVK_OK;
+}
+
+int bevk_host_alloc(uint64_t bytes, void** out) {
+  if (!out) return fail(BEVK_ERR_ARG, "null out");
+  CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return BEVK_OK;
+}
+int bevk_host_free(void* p) {
+  if (p) CU(cudaFreeHost(p));
+  return BEVK_OK;
+}
+
+// ------------------------------------------------------------------ K1
+int bevk_undistort_map(bevk_ctx* c, int model, const double K[9], const double* D, int n_dist, const double P[9], int w,
+                       int h, int16_t* map1, uint16_t* map2) {
+  RET(use(c));
+  if (!map1 || !map2) return fail(BEVK_ERR_ARG, "null output map");
+  CamModel cm;
+  RET(make_model(model, K, D, n_dist, P, w, h, &cm));
+  const size_t n = (size_t)w * h;
+  RET(c->s_m1.ensure(n * 4));
+  RET(c->s_m2.ensure(n * 2));
+  k_undistort_map<<<grid2d(w, h), 256, 0, c->stream>>>(cm, c->s_m1.as<short2>(), c->s_m2.as<unsigned short>());
+  LAUNCHED(c);
+  CU(cudaMemcpyAsync(map1, c->s_m1.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(map2, c->s_m2.p, n * 2, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BEVK_OK;
+}
+
+// ------------------------------------------------------------------ gather dispatch
+template <int MODE>
+static int launch_gather(bevk_ctx* c, const GatherArgs& a, int channels, int interp) {
+  const dim3 g = grid2d(a.dw, a.dh);
+#define GO(C, L) k_gather<MODE, C, L><<<g, 256, 0, c->stream>>>(a)
+  if (interp == BEVK_INTER_LINEAR) {
+    if (channels == 1) GO(1, 1); else if (channels == 3) GO(3, 1); else GO(4, 1);
+  } else {
+    if (channels == 1) GO(1, 0); else if (channels == 3) GO(3, 0); else GO(4, 0);
+  }
+#undef GO
+  LAUNCHED(c);
+  return BEVK_OK;
+}
+
+static int check_image(const void* p, int w, int h, int64_t stride, int channels, const char* what) {
+  if (!p) return fail(BEVK_ERR_ARG, "null %s", what);
+  if (w <= 0 || h <= 0) return fail(BEVK_ERR_ARG, "bad %s size %dx%d", what, w, h);
+  if (channels != 1 && channels != 3 && channels != 4) return fail(BEVK_ERR_UNSUPPORTED, "channels must be 1, 3 or 4");
+  if (stride < (int64_t)w * channels) return fail(BEVK_ERR_ARG, "%s stride %lld < row bytes", what, (long long)stride);
+  return BEVK_OK;
+}
+
+static int upload_image(bevk_ctx* c, DevBuf& buf, const uint8_t* src, int w, int h, int64_t stride, int channels) {
+  const size_t row = (size_t)w * channels;
+  RET(buf.ensure(row * h));
+  CU(cudaMemcpy2DAsync(buf.p, row, src, (size_t)stride, row, h, cudaMemcpyHostToDevice, c->stream));
+  return BEVK_OK;
+}
+static int download_image(bevk_ctx* c, const DevBuf& buf, uint8_t* dst, int w, int h, int64_t stride, int channels) {
+  const size_t row = (size_t)w * channels;
+  CU(cudaMemcpy2DAsync(dst, (size_t)stride, buf.p, row, row, h, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BEVK_OK;
+}
+
+int bevk_remap(bevk_ctx* c, const uint8_t* src, int sw, int sh, int64_t sstride, int channels, const int16_t* map1,
+               const uint16_t* map2, int dw, int dh, uint8_t* dst, int64_t dstride, int interp) {
+  RET(use(c));
+  RET(check_image(src, sw, sh, sstride, channels, "src"));
+  RET(check_image(dst, dw, dh, dstride, channels, "dst"));
+  if (!map1) return fail(BEVK_ERR_ARG, "null map1");
+  if (interp == BEVK_INTER_LINEAR && !map2) return fail(BEVK_ERR_ARG, "INTER_LINEAR needs map2");
+  if (interp != BEVK_INTER_LINEAR && interp != BEVK_INTER_NEAREST) return fail(BEVK_ERR_UNSUPPORTED, "interp %d", interp);
+  const size_t n = (size_t)dw * dh;
+  RET(upload_image(c, c->s_src, src, sw, sh, sstride, channels));
+  RET(c->s_m1.ensure(n * 4));
+  RET(c->s_m2.ensure(n * 2));
+  RET(c->s_dst.ensure(n * channels));
+  CU(cudaMemcpyAsync(c->s_m1.p, map1, n * 4, cudaMemcpyHostToDevice, c->stream));
+  if (map2) CU(cudaMemcpyAsync(c->s_m2.p, map2, n * 2, cudaMemcpyHostToDevice, c->stream));
+  GatherArgs a{};
+  a.src = c->s_src.as<uint8_t>(); a.sw = sw; a.sh = sh; a.spitch = (long long)sw * channels;
+  a.dst = c->s_dst.as<uint8_t>(); a.dw = dw; a.dh = dh; a.dpitch = (long long)dw * channels;
+  a.map1 = c->s_m1.as<short2>(); a.map2 = map2 ? c->s_m2.as<unsigned short>() : nullptr;
+  RET(launch_gather<0>(c, a, channels, interp));
+  return download_image(c, c->s_dst, dst, dw, dh, dstride, channels);
+}
+
+// ------------------------------------------------------------------ cached-map undistortion
+int bevk_undistorter_set(bevk_ctx* c, int slot, int model, const double K[9], const double* D, int n_dist,
+                         const double P[9], int dw, int dh, int fused) {
+  RET(use(c));
+  if (slot < 0 || slot >= 8) return fail(BEVK_ERR_ARG, "slot %d out of range", slot);
+  Undistorter& u = c->und[slot];
+  u.valid = false;
+  RET(make_model(model, K, D, n_dist, P, dw, dh, &u.cm));
+  u.fused = fused != 0;
+  if (!u.fused) {
+    const size_t n = (size_t)dw * dh;
+    RET(u.map1.ensure(n * 4));
+    RET(u.map2.ensure(n * 2));
+    k_undistort_map<<<grid2d(dw, dh), 256, 0, c->stream>>>(u.cm, u.map1.as<short2>(), u.map2.as<unsigned short>());
+    LAUNCHED(c);
+  }
+  u.valid = true;
+  return BEVK_OK;
+}
+
+int bevk_undistorter_maps(bevk_ctx* c, int slot, int16_t* map1, uint16_t* map2) {
+  RET(use(c));
+  if (slot < 0 || slot >= 8 || !c->und[slot].valid) return fail(BEVK_ERR_ARG, "undistorter slot %d not set", slot);
+  if (!map1 || !map2) return fail(BEVK_ERR_ARG, "null output map");
+  Undistorter& u = c->und[slot];
+  const size_t n = (size_t)u.cm.w * u.cm.h;
+  const short2* m1 = u.map1.as<short2>();
+  const unsigned short* m2 = u.map2.as<unsigned short>();
+  if (u.fused) {   // no resident map: evaluate into scratch
+    RET(c->s_m1.ensure(n * 4));
+    RET(c->s_m2.ensure(n * 2));
+    k_undistort_map<<<grid2d(u.cm.w, u.cm.h), 256, 0, c->stream>>>(u.cm, c->s_m1.as<short2>(), c->s_m2.as<unsigned short>());
+    LAUNCHED(c);
+    m1 = c->s_m1.as<short2>(); m2 = c->s_m2.as<unsigned short>();
+  }
+  CU(cudaMemcpyAsync(map1, m1, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(map2, m2, n * 2, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BEVK_OK;
+}
+
+int bevk_undistort(bevk_ctx* c, int slot, const uint8_t* src, int sw, int sh, int64_t sstride, int channels,
+                   uint8_t* dst, int64_t dstride, int interp) {
+  RET(use(c));
+  if (slot < 0 || slot >= 8 || !c->und[slot].valid) return fail(BEVK_ERR_ARG, "undistorter slot %d not set", slot);
+  Undistorter& u = c->und[slot];
+  const int dw = u.cm.w, dh = u.cm.h;
+  RET(check_image(src, sw, sh, sstride, channels, "src"));
+  RET(check_image(dst, dw, dh, dstride, channels, "dst"));
+  if (interp != BEVK_INTER_LINEAR && interp != BEVK_INTER_NEAREST) return fail(BEVK_ERR_UNSUPPORTED, "interp %d", interp);
+  RET(upload_image(c, c->s_src, src, sw, sh, sstride, channels));
+  RET(c->s_dst.ensure((size_t)dw * dh * channels));
+  GatherArgs a{};
+  a.src = c->s_src.as<uint8_t>(); a.sw = sw; a.sh = sh; a.spitch = (long long)sw * channels;
+  a.dst = c->s_dst.as<uint8_t>(); a.dw = dw; a.dh = dh; a.dpitch = (long long)dw * channels;
+  if (u.fused) {
+    a.cm = u.cm;
+    RET(launch_gather<1>(c, a, channels, interp));
+  } else {
+    a.map1 = u.map1.as<short2>(); a.map2 = u.map2.as<unsigned short>();
+    RET(launch_gather<0>(c, a, channels, interp));
+  }
+  return download_image(c, c->s_dst, dst, dw, dh, dstride, channels);
+}
+
+// ------------------------------------------------------------------ K4 / K2
+int bevk_warp_perspective(bevk_ctx* c, const uint8_t* src, int sw, int sh, int64_t sstride, int channels,
+                          const double H[9], uint8_t* dst, int dw, int dh, int64_t dstride, int interp) {
+  RET(use(c));
+  RET(check_image(src, sw, sh, sstride, channels, "src"));
+  RET(check_image(dst, dw, dh, dstride, channels, "dst"));
+  if (interp != BEVK_INTER_LINEAR && interp != BEVK_INTER_NEAREST) return fail(BEVK_ERR_UNSUPPORTED, "interp %d", interp);
+  GatherArgs a{};
+  RET(make_homog(H, &a.hm));
+  RET(upload_image(c, c->s_src, src, sw, sh, sstride, channels));
+  RET(c->s_dst.ensure((size_t)dw * dh * channels));
+  a.src = c->s_src.as<uint8_t>(); a.sw = sw; a.sh = sh; a.spitch = (long long)sw * channels;
+  a.dst = c->s_dst.as<uint8_t>(); a.dw = dw; a.dh = dh; a.dpitch = (long long)dw * channels;
+  RET(launch_gather<2>(c, a, channels, interp));
+  return download_image(c, c->s_dst, dst, dw, dh, dstride, channels);
+}
+
+int bevk_warp_maps(bevk_ctx* c, const int16_t* map1, const uint16_t* map2, int sw, int sh, const double H[9], int dw,
+                   int dh, int16_t* out1, uint16_t* out2) {
+  RET(use(c));
+  if (!map1 || !map2 || !out1 || !out2) return fail(BEVK_ERR_ARG, "null map pointer");
+  if (sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0) return fail(BEVK_ERR_ARG, "bad size");
+  WarpMapsArgs a{};
+  RET(make_homog(H, &a.hm));
+  const size_t ns = (size_t)sw * sh, nd = (size_t)dw * dh;
+  RET(c->s_m1.ensure(ns * 4));
+  RET(c->s_m2.ensure(ns * 2));
+  RET(c->s_o1.ensure(nd * 4));
+  RET(c->s_o2.ensure(nd * 2));
+  CU(cudaMemcpyAsync(c->s_m1.p, map1, ns * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->s_m2.p, map2, ns * 2, cudaMemcpyHostToDevice, c->stream));
+  a.in1 = c->s_m1.as<short2>(); a.in2 = c->s_m2.as<unsigned short>(); a.sw = sw; a.sh = sh;
+  a.out1 = c->s_o1.as<short2>(); a.out2 = c->s_o2.as<unsigned short>(); a.dw = dw; a.dh = dh;
+  k_warp_maps<0><<<grid2d(dw, dh), 256, 0, c->stream>>>(a);
+  LAUNCHED(c);
+  CU(cudaMemcpyAsync(out1, c->s_o1.p, nd * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(out2, c->s_o2.p, nd * 2, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BEVK_OK;
+}
+
+// ------------------------------------------------------------------ BEV engine: setup
+int bevk_bev_configure(bevk_ctx* c, int n_cam, int fw, int fh, int bw, int bh) {
+  RET(use(c));
+  if (n_cam < 1 || n_cam > BEVK_MAX_CAMERAS) return fail(BEVK_ERR_ARG, "n_cam %d out of range", n_cam);
+  if (fw <= 0 || fh <= 0 || bw <= 0 || bh <= 0) return fail(BEVK_ERR_ARG, "bad geometry");
+  if (fw > 32767 || fh > 32767) return fail(BEVK_ERR_UNSUPPORTED, "frames larger than 32767 px");
+  if ((long long)fw * fh * 3 + 16 > 0xffffffffLL) return fail(BEVK_ERR_UNSUPPORTED, "frame too large for 32-bit offsets");
+  c->n_cam = n_cam; c->FW = fw; c->FH = fh; c->BW = bw; c->BH = bh;
+  c->planned = false;
+  for (auto& k : c->cam) { k.has_maps = false; k.has_mask = false; k.mask.clear(); }
+  return BEVK_OK;
+}
+
+static int need_cam(bevk_ctx* c, int cam) {
+  if (c->n_cam == 0) return fail(BEVK_ERR_ARG, "bevk_bev_configure not called");
+  if (cam < 0 || cam >= c->n_cam) return fail(BEVK_ERR_ARG, "camera %d out of range", cam);
+  return BEVK_OK;
+}
+
+int bevk_bev_set_camera(bevk_ctx* c, int cam, const double K[9], const double D[4], const double P[9], int und_w,
+                        int und_h, const double H[9]) {
+  RET(use(c));
+  RET(need_cam(c, cam));
+  WarpMapsArgs a{};
+  RET(make_model(BEVK_MODEL_FISHEYE, K, D, 4, P, und_w, und_h, &a.cm));
+  RET(make_homog(H, &a.hm));
+  BevCam& k = c->cam[cam];
+  const size_t n = (size_t)c->BW * c->BH;
+  RET(k.map1.ensure(n * 4));
+  RET(k.map2.ensure(n * 2));
+  a.sw = und_w; a.sh = und_h;
+  a.out1 = k.map1.as<short2>(); a.out2 = k.map2.as<unsigned short>(); a.dw = c->BW; a.dh = c->BH;
+  k_warp_maps<1><<<grid2d(c->BW, c->BH), 256, 0, c->stream>>>(a);
+  LAUNCHED(c);
+  k.has_maps = true;
+  c->planned = false;
+  return BEVK_OK;
+}
+
+int bevk_bev_set_maps(bevk_ctx* c, int cam, const int16_t* map1, const uint16_t* map2) {
+  RET(use(c));
+  RET(need_cam(c, cam));
+  if (!map1 || !map2) return fail(BEVK_ERR_ARG, "null map");
+  BevCam& k = c->cam[cam];
+  const size_t n = (size_t)c->BW * c->BH;
+  RET(k.map1.ensure(n * 4));
+  RET(k.map2.ensure(n * 2));
+  CU(cudaMemcpyAsync(k.map1.p, map1, n * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(k.map2.p, map2, n * 2, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  k.has_maps = true;
+  c->planned = false;
+  return BEVK_OK;
+}
+
+int bevk_bev_get_maps(bevk_ctx* c, int cam, int16_t* map1, uint16_t* map2) {
+  RET(use(c));
+  RET(need_cam(c, cam));
+  BevCam& k = c->cam[cam];
+  if (!k.has_maps) return fail(BEVK_ERR_ARG, "camera %d has no maps", cam);
+  if (!map1 || !map2) return fail(BEVK_ERR_ARG, "null map");
+  const size_t n = (size_t)c->BW * c->BH;
+  CU(cudaMemcpyAsync(map1, k.map1.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(map2, k.map2.p, n * 2, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BEVK_OK;
+}
+
+int bevk_bev_set_mask(bevk_ctx* c, int cam, const uint8_t* mask) {
+  RET(use(c));
+  RET(need_cam(c, cam));
+  if (!mask) return fail(BEVK_ERR_ARG, "null mask");
+  BevCam& k = c->cam[cam];
+  k.mask.assign(mask, mask + (size_t)c->BW * c->BH);
+  k.has_mask = true;
+  c->planned = false;
+  return BEVK_OK;
+}
+
+int bevk_blend_masks(bevk_ctx* c, const uint8_t* polys, const int32_t* lines, int bw, int bh, uint8_t* out) {
+  RET(use(c));
+  if (!polys || !lines || !out) return fail(BEVK_ERR_ARG, "null argument");
+  if (bw <= 0 || bh <= 0) return fail(BEVK_ERR_ARG, "bad size");
+  const size_t n = (size_t)bw * bh * 4;
+  RET(c->s_src.ensure(n));
+  RET(c->s_dst.ensure(n));
+  CU(cudaMemcpyAsync(c->s_src.p, polys, n, cudaMemcpyHostToDevice, c->stream));
+  BlendArgs a{};
+  a.polys = c->s_src.as<uint8_t>(); a.out = c->s_dst.as<uint8_t>(); a.w = bw; a.h = bh;
+  for (int i = 0; i < 8; ++i) for (int j = 0; j < 4; ++j) a.lines[i][j] = lines[i * 4 + j];
+  k_blend_masks<<<grid2d(bw, bh), 256, 0, c->stream>>>(a);
+  LAUNCHED(c);
+  CU(cudaMemcpyAsync(out, c->s_dst.p, n, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BEVK_OK;
+}
+
+// Tile-plan compiler: LUT maps + masks -> per-tile item lists and thread-ordered LUT blocks.
+int bevk_bev_finalize(bevk_ctx* c) {
+  RET(use(c));
+  if (c->n_cam == 0) return fail(BEVK_ERR_ARG, "bevk_bev_configure not called");
+  const int BW = c->BW, BH = c->BH, FW = c->FW, FH = c->FH, NC = c->n_cam;
+  const size_t npx = (size_t)BW * BH;
+  std::vector<std::vector<short>> m1(NC);
+  std::vector<std::vector<unsigned short>> m2(NC);
+  for (int k = 0; k < NC; ++k) {
+    if (!c->cam[k].has_maps) return fail(BEVK_ERR_ARG, "camera %d has no maps", k);
+    if (!c->cam[k].has_mask) return fail(BEVK_ERR_ARG, "camera %d has no mask", k);
+    m1[k].resize(npx * 2);
+    m2[k].resize(npx);
+    CU(cudaMemcpyAsync(m1[k].data(), c->cam[k].map1.p, npx * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(m2[k].data(), c->cam[k].map2.p, npx * 2, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  const unsigned pitch = (unsigned)FW * 3u;
+  const long long frame_bytes = (long long)pitch * FH;
+  const int tx = (BW + TILE - 1) / TILE, ty = (BH + TILE - 1) / TILE;
+  std::vector<int4> tiles;
+  std::vector<int2> items;
+  std::vector<uint2> lut;
+  tiles.reserve((size_t)tx * ty);
+  for (int tj = 0; tj < ty; ++tj)
+    for (int ti = 0; ti < tx; ++ti) {
+      const int x0 = ti * TILE, y0 = tj * TILE;
+      int4 t = make_int4(x0, y0, (int)items.size(), 0);
+      for (int k = 0; k < NC; ++k) {
+        const uint8_t* mk = c->cam[k].mask.data();
+        bool any = false;
+        long long cx = 0, cy = 0;   // source-row changes along canvas x vs canvas y
+        for (int y = y0; y < std::min(y0 + TILE, BH); ++y)
+          for (int x = x0; x < std::min(x0 + TILE, BW); ++x) {
+            const size_t p = (size_t)y * BW + x;
+            if (!mk[p]) continue;
+            any = true;
+            const int sy = m1[k][2 * p + 1];
+            if (x + 1 < BW && mk[p + 1]) cx += std::abs(m1[k][2 * (p + 1) + 1] - sy);
+            if (y + 1 < BH && mk[p + BW]) cy += std::abs(m1[k][2 * (p + BW) + 1] - sy);
+          }
+        if (!any) continue;
+        const int orient = cy < cx ? 1 : 0;
+        const size_t base = lut.size();
+        lut.resize(base + TILE * TILE, make_uint2(0u, 0u));
+        for (int kk = 0; kk < 4; ++kk)
+          for (int th = 0; th < 256; ++th) {
+            const int lane = th & 31, major = (th >> 5) * 4 + kk;
+            const int x = x0 + (orient ? major : lane), y = y0 + (orient ? lane : major);
+            if (x >= BW || y >= BH) continue;
+            const size_t p = (size_t)y * BW + x;
+            const unsigned w = mk[p];
+            if (!w) continue;
+            const int sx = m1[k][2 * p], sy = m1[k][2 * p + 1];
+            const unsigned frac = m2[k][p] & 1023u;
+            uint2 e;
+            e.y = frac | (w << 16) | LUT_ACTIVE;
+            const bool inside = sx >= 0 && sy >= 0 && sx + 1 < FW && sy + 1 < FH;
+            const long long off = (long long)sy * pitch + (long long)sx * 3;
+            if (!inside || off + pitch + 12 > frame_bytes) {
+              e.y |= LUT_BORDER;
+              e.x = (unsigned)(unsigned short)sx | ((unsigned)(unsigned short)sy << 16);
+            } else {
+              e.x = (unsigned)off;
+            }
+            lut[base + kk * 256 + th] = e;
+          }
+        items.push_back(make_int2(k, orient));
+        t.w++;
+      }
+      tiles.push_back(t);
+    }
+  c->n_tiles = (long long)tiles.size();
+  c->n_items = (long long)items.size();
+  RET(c->d_tiles.ensure(tiles.size() * sizeof(int4)));
+  RET(c->d_items.ensure(std::max<size_t>(1, items.size()) * sizeof(int2)));
+  RET(c->d_lut.ensure(std::max<size_t>(1, lut.size()) * sizeof(uint2)));
+  CU(cudaMemcpyAsync(c->d_tiles.p, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+  if (!items.empty()) {
+    CU(cudaMemcpyAsync(c->d_items.p, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_lut.p, lut.data(), lut.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+  }
+  // OpenCV's 8-bit HSV division tables (color_hsv: sdiv_table / hdiv_table180, hsv_shift = 12)
+  std::vector<int> tab(512, 0);
+  for (int i = 1; i < 256; ++i) {
+    tab[i] = (int)std::nearbyint((255 << 12) / (1. * i));
+    tab[256 + i] = (int)std::nearbyint((180 << 12) / (6. * i));
+  }
+  RET(c->d_hsv.ensure(512 * sizeof(int)));
+  CU(cudaMemcpyAsync(c->d_hsv.p, tab.data(), 512 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->planned = true;
+  return BEVK_OK;
+}
+
+int bevk_bev_plan_info(bevk_ctx* c, int64_t* n_tiles, int64_t* n_items, int64_t* lut_bytes) {
+  RET(use(c));
+  if (!c->planned) return fail(BEVK_ERR_ARG, "bevk_bev_finalize not called");
+  if (n_tiles) *n_tiles = c->n_tiles;
+  if (n_items) *n_items = c->n_items;
+  if (lut_bytes) *lut_bytes = c->n_items * TILE * TILE * (int64_t)sizeof(uint2);
+  return BEVK_OK;
+}
+
+// ------------------------------------------------------------------ BEV engine: run
+static int run_device(bevk_ctx* c, const void* d_srcs, int batch, const void* d_car, int flags, void* d_out, int cam_lo,
+                      int cam_hi) {
+  if (!c->planned) return fail(BEVK_ERR_ARG, "bevk_bev_finalize not called");
+  if (!d_srcs || !d_out) return fail(BEVK_ERR_ARG, "null device pointer");
+  if (batch < 1 || batch > 65535) return fail(BEVK_ERR_ARG, "batch %d out of range [1,65535]", batch);
+  const bool bal = (flags & BEVK_FLAG_BALANCE) != 0;
+  BevParams P{};
+  P.srcs = reinterpret_cast<const uint8_t* const*>(d_srcs);
+  P.n_cam = c->n_cam; P.FW = c->FW; P.FH = c->FH; P.pitch = (unsigned)c->FW * 3u;
+  P.tiles = c->d_tiles.as<int4>(); P.items = c->d_items.as<int2>(); P.lut = c->d_lut.as<uint2>();
+  P.out = reinterpret_cast<uint8_t*>(d_out); P.BW = c->BW; P.BH = c->BH;
+  P.canvas_bytes = (long long)c->BW * c->BH * 3;
+  P.car = reinterpret_cast<const uint8_t*>(d_car);
+  P.hsv_tab = c->d_hsv.as<int>();
+  P.cam_lo = cam_lo; P.cam_hi = cam_hi;
+  P.tail_start = c->FW - (c->FW % 32);
+  P.wide = (P.pitch % 4 == 0) ? 1 : 0;   // frames from cudaMalloc / torch are >= 256-B aligned
+  if (c->timed) CU(cudaEventRecord(c->ev0, c->stream));
+  if (bal) {
+    const int nf = batch * c->n_cam;
+    RET(c->d_vsum.ensure((size_t)nf * 8));
+    RET(c->d_delta.ensure((size_t)nf * 4));
+    RET(c->d_csum.ensure((size_t)batch * 24));
+    CU(cudaMemsetAsync(c->d_vsum.p, 0, (size_t)nf * 8, c->stream));
+    CU(cudaMemsetAsync(c->d_csum.p, 0, (size_t)batch * 24, c->stream));
+    const long long frame_bytes = (long long)P.pitch * c->FH;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(148 * 4 / std::max(1, std::min(nf, 64)) + 1, frame_bytes / (48 * 256) + 1));
+    k_vsum<<<dim3(blocks, nf), 256, 0, c->stream>>>(P.srcs, frame_bytes, c->d_vsum.as<unsigned long long>());
+    LAUNCHED(c);
+    k_delta<<<(batch + 127) / 128, 128, 0, c->stream>>>(c->d_vsum.as<unsigned long long>(), c->n_cam, batch,
+                                                         (double)c->FW * (double)c->FH, c->d_delta.as<int>());
+    LAUNCHED(c);
+    P.delta = c->d_delta.as<int>();
+    P.csum = c->d_csum.as<unsigned long long>();
+    k_bev<true><<<dim3((unsigned)c->n_tiles, batch), 256, 0, c->stream>>>(P);
+    LAUNCHED(c);
+    const int gblocks = (int)std::max<long long>(1, std::min<long long>(P.canvas_bytes / (12 * 256) + 1, 148 * 8 / std::max(1, std::min(batch, 64)) + 1));
+    k_gain<<<dim3(gblocks, batch), 256, 0, c->stream>>>(P.out, P.canvas_bytes, (double)c->BW * (double)c->BH,
+                                                        c->d_csum.as<unsigned long long>(), P.car);
+    LAUNCHED(c);
+  } else {
+    k_bev<false><<<dim3((unsigned)c->n_tiles, batch), 256, 0, c->stream>>>(P);
+    LAUNCHED(c);
+  }
+  if (c->timed) CU(cudaEventRecord(c->ev1, c->stream));
+  return BEVK_OK;
+}
+
+int bevk_bev_run_device(bevk_ctx* c, const void* d_srcs, int batch, const void* d_car, int flags, void* d_out) {
+  RET(use(c));
+  c->timed = true;
+  return run_device(c, d_srcs, batch, d_car, flags, d_out, 0, BEVK_MAX_CAMERAS);
+}
+
+int bevk_bev_run_device_cams(bevk_ctx* c, const void* d_srcs, int batch, int cam_lo, int cam_hi, void* d_out) {
+  RET(use(c));
+  if (cam_lo < 0 || cam_hi > c->n_cam || cam_lo > cam_hi) return fail(BEVK_ERR_ARG, "bad camera range [%d,%d)", cam_lo, cam_hi);
+  c->timed = true;
+  return run_device(c, d_srcs, batch, nullptr, 0, d_out, cam_lo, cam_hi);
+}
+
+int bevk_sat_sum_device(bevk_ctx* c, const void* const* parts, int n, uint64_t bytes, const void* d_car, void* d_out) {
+  RET(use(c));
+  if (!parts || !d_out || n < 1 || n > BEVK_MAX_CAMERAS) return fail(BEVK_ERR_ARG, "bad partial list");
+  SatSumArgs a{};
+  for (int i = 0; i < n; ++i) {
+    if (!parts[i] || (reinterpret_cast<uintptr_t>(parts[i]) & 15)) return fail(BEVK_ERR_ARG, "partial %d null or not 16-B aligned", i);
+    a.parts[i] = reinterpret_cast<const uint8_t*>(parts[i]);
+  }
+  if ((reinterpret_cast<uintptr_t>(d_out) & 15) || (d_car && (reinterpret_cast<uintptr_t>(d_car) & 15)))
+    return fail(BEVK_ERR_ARG, "out/car not 16-B aligned");
+  a.n = n; a.bytes = bytes; a.car = reinterpret_cast<const uint8_t*>(d_car); a.out = reinterpret_cast<uint8_t*>(d_out);
+  const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>(148 * 8, bytes / (16 * 256) + 1));
+  k_sat_sum<<<blocks, 256, 0, c->stream>>>(a);
+  LAUNCHED(c);
+  return BEVK_OK;
+}
+
+int bevk_bev_run(bevk_ctx* c, const uint8_t* const* srcs, int64_t src_stride, int batch, const uint8_t* car, int flags,
+                 uint8_t* out) {
+  RET(use(c));
+  if (!c->planned) return fail(BEVK_ERR_ARG, "bevk_bev_finalize not called");
+  if (!srcs || !out) return fail(BEVK_ERR_ARG, "null host pointer");
+  if (batch < 1) return fail(BEVK_ERR_ARG, "batch must be >= 1");
+  const size_t row = (size_t)c->FW * 3, fbytes = row * c->FH, fpad = (fbytes + 255) & ~size_t(255);
+  if (src_stride < (int64_t)row) return fail(BEVK_ERR_ARG, "src_stride %lld < row bytes", (long long)src_stride);
+  const size_t cbytes = (size_t)c->BW * c->BH * 3;
+  const int chunk_max = 64;   // frame-sets resident at once (64 x 4 x 1080p = 1.6 GB)
+  const int chunk = std::min(batch, chunk_max);
+  RET(c->d_frames.ensure(fpad * c->n_cam * chunk));
+  RET(c->d_ptrs.ensure(sizeof(void*) * c->n_cam * chunk));
+  RET(c->d_canvas.ensure(cbytes * chunk));
+  if (car) {
+    RET(c->d_car.ensure(cbytes));
+    CU(cudaMemcpyAsync(c->d_car.p, car, cbytes, cudaMemcpyHostToDevice, c->stream));
+  }
+  {
+    std::vector<const uint8_t*> ptrs((size_t)c->n_cam * chunk);
+    for (size_t i = 0; i < ptrs.size(); ++i) ptrs[i] = c->d_frames.as<uint8_t>() + i * fpad;
+    CU(cudaMemcpyAsync(c->d_ptrs.p, ptrs.data(), ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));   // ptrs is a stack-lifetime staging vector
+  }
+  for (int b0 = 0; b0 < batch; b0 += chunk) {
+    const int nb = std::min(chunk, batch - b0);
+    for (int i = 0; i < nb * c->n_cam; ++i) {
+      const uint8_t* s = srcs[(size_t)b0 * c->n_cam + i];
+      if (!s) return fail(BEVK_ERR_ARG, "null frame pointer %d", b0 * c->n_cam + i);
+      uint8_t* d = c->d_frames.as<uint8_t>() + (size_t)i * fpad;
+      if ((size_t)src_stride == row) CU(cudaMemcpyAsync(d, s, fbytes, cudaMemcpyHostToDevice, c->stream));
+      else CU(cudaMemcpy2DAsync(d, row, s, (size_t)src_stride, row, c->FH, cudaMemcpyHostToDevice, c->stream));
+    }
+    c->timed = false;
+    RET(run_device(c, c->d_ptrs.p, nb, car ? c->d_car.p : nullptr, flags, c->d_canvas.p, 0, BEVK_MAX_CAMERAS));
+    CU(cudaMemcpyAsync(out + (size_t)b0 * cbytes, c->d_canvas.p, cbytes * nb, cudaMemcpyDeviceToHost, c->stream));
+    if (b0 + chunk < batch) CU(cudaStreamSynchronize(c->stream));   // the frame buffers are reused by the next chunk
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return BEVK_OK;
+}
+
+// ------------------------------------------------------------------ stand-alone helpers
+static int ensure_hsv(bevk_ctx* c) {
+  if (c->d_hsv.p) return BEVK_OK;
+  std::vector<int> tab(512, 0);
+  for (int i = 1; i < 256; ++i) {
+    tab[i] = (int)std::nearbyint((255 << 12) / (1. * i));
+    tab[256 + i] = (int)std::nearbyint((180 << 12) / (6. * i));
+  }
+  RET(c->d_hsv.ensure(512 * sizeof(int)));
+  CU(cudaMemcpyAsync(c->d_hsv.p, tab.data(), 512 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BEVK_OK;
+}
+
+static int stream_blocks(long long n_items) {
+  return (int)std::max<long long>(1, std::min<long long>(148 * 8, (n_items + 255) / 256));
+}
+
+int bevk_apply_mask(bevk_ctx* c, const uint8_t* img, const uint8_t* mask, int w, int h, int blend, uint8_t* out) {
+  RET(use(c));
+  if (!img || !mask || !out || w <= 0 || h <= 0) return fail(BEVK_ERR_ARG, "bad argument");
+  const size_t npx = (size_t)w * h;
+  RET(c->s_src.ensure(npx * 3));
+  RET(c->s_m1.ensure(npx));
+  RET(c->s_dst.ensure(npx * 3));
+  CU(cudaMemcpyAsync(c->s_src.p, img, npx * 3, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->s_m1.p, mask, npx, cudaMemcpyHostToDevice, c->stream));
+  k_apply_mask<<<stream_blocks(npx), 256, 0, c->stream>>>(c->s_src.as<uint8_t>(), c->s_m1.as<uint8_t>(),
+                                                          c->s_dst.as<uint8_t>(), (long long)npx, blend);
+  LAUNCHED(c);
+  CU(cudaMemcpyAsync(out, c->s_dst.p, npx * 3, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BEVK_OK;
+}
+
+int bevk_color_balance(bevk_ctx* c, const uint8_t* img, int w, int h, uint8_t* out) {
+  RET(use(c));
+  if (!img || !out || w <= 0 || h <= 0) return fail(BEVK_ERR_ARG, "bad argument");
+  const size_t npx = (size_t)w * h;
+  RET(c->s_dst.ensure(npx * 3));
+  RET(c->d_csum.ensure(24));
+  CU(cudaMemcpyAsync(c->s_dst.p, img, npx * 3, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(c->d_csum.p, 0, 24, c->stream));
+  k_chan_sum<<<stream_blocks(npx), 256, 0, c->stream>>>(c->s_dst.as<uint8_t>(), (long long)npx,
+                                                        c->d_csum.as<unsigned long long>());
+  LAUNCHED(c);
+  k_gain<<<dim3(stream_blocks(npx / 4 + 1), 1), 256, 0, c->stream>>>(c->s_dst.as<uint8_t>(), (long long)npx * 3, (double)npx,
+                                                                   c->d_csum.as<unsigned long long>(), nullptr);
+  LAUNCHED(c);
+  CU(cudaMemcpyAsync(out, c->s_dst.p, npx * 3, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BEVK_OK;
+}
+
+int bevk_luminance_balance(bevk_ctx* c, const uint8_t* const* imgs, int n, int w, int h, uint8_t* const* outs) {
+  RET(use(c));
+  if (!imgs || !outs || n < 1 || n > BEVK_MAX_CAMERAS || w <= 0 || h <= 0) return fail(BEVK_ERR_ARG, "bad argument");
+  RET(ensure_hsv(c));
+  const size_t fbytes = (size_t)w * h * 3, fpad = (fbytes + 255) & ~size_t(255);
+  RET(c->s_src.ensure(fpad * n));
+  RET(c->s_dst.ensure(fpad * n));
+  RET(c->d_ptrs.ensure(sizeof(void*) * 2 * BEVK_MAX_CAMERAS));
+  RET(c->d_vsum.ensure(8 * n));
+  RET(c->d_delta.ensure(4 * n));
+  const uint8_t* ptrs[2 * BEVK_MAX_CAMERAS];
+  for (int i = 0; i < n; ++i) {
+    if (!imgs[i] || !outs[i]) return fail(BEVK_ERR_ARG, "null frame %d", i);
+    ptrs[i] = c->s_src.as<uint8_t>() + i * fpad;
+    ptrs[BEVK_MAX_CAMERAS + i] = c->s_dst.as<uint8_t>() + i * fpad;
+    CU(cudaMemcpyAsync(const_cast<uint8_t*>(ptrs[i]), imgs[i], fbytes, cudaMemcpyHostToDevice, c->stream));
+  }
+  CU(cudaMemcpyAsync(c->d_ptrs.p, ptrs, sizeof ptrs, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(c->d_vsum.p, 0, 8 * n, c->stream));
+  const uint8_t* const* d_in = c->d_ptrs.as<const uint8_t*>();
+  uint8_t* const* d_out = reinterpret_cast<uint8_t* const*>(c->d_ptrs.as<uint8_t*>() + BEVK_MAX_CAMERAS);
+  k_vsum<<<dim3(stream_blocks(fbytes / 48 + 1) / n + 1, n), 256, 0, c->stream>>>(d_in, (long long)fbytes,
+                                                                                 c->d_vsum.as<unsigned long long>());
+  LAUNCHED(c);
+  k_delta<<<1, 32, 0, c->stream>>>(c->d_vsum.as<unsigned long long>(), n, 1, (double)w * (double)h, c->d_delta.as<int>());
+  LAUNCHED(c);
+  k_lum_apply<<<dim3(stream_blocks((long long)w * h) / n + 1, n), 256, 0, c->stream>>>(d_in, d_out, w, h, c->d_delta.as<int>(),
+                                                                                       c->d_hsv.as<int>());
+  LAUNCHED(c);
+  for (int i = 0; i < n; ++i)
+    CU(cudaMemcpyAsync(outs[i], ptrs[BEVK_MAX_CAMERAS + i], fbytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));   // also keeps the stack-resident ptrs[] alive long enough
+  return BEVK_OK;
+}
+
+int64_t bevk_launch_count(bevk_ctx* c) { return c ? c->launches : 0; }
+
+int bevk_last_kernel_ms(bevk_ctx* c, float* ms) {
+  RET(use(c));
+  if (!ms) return fail(BEVK_ERR_ARG, "null ms");
+  if (!c->timed) return fail(BEVK_ERR_ARG, "no timed bevk_bev_run_device call yet");
+  CU(cudaEventSynchronize(c->ev1));
+  CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return BEVK_OK;
+}
+

@@ -1,0 +1,157 @@
+// bevk_device.cuh -- device-side arithmetic shared by the bevk kernels (sm_100a).
+//
+// Everything here is a bit-exact restatement target: the coordinate math is IEEE
+// FP64 with NO fused multiply-add (OpenCV's x86 baseline build has none), so every
+// product/sum goes through __dmul_rn/__dadd_rn, which the compiler may not contract.
+// Specs: SURVEY.md Appendix A1 (fisheye map), A11 (pinhole map), A2 (fixed-point
+// bilinear), A3 (warpPerspective coordinates), A9 (8-bit HSV round trip).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bevk {
+
+constexpr int INTER_BITS = 5;
+constexpr int TAB = 32;
+
+struct CamModel {      // cv2.fisheye / cv2 initUndistortRectifyMap inputs, pre-digested on the host
+  double iR[9];        // inv(P * R), R = I
+  double k[5];         // fisheye: k1..k4 ; pinhole: k1,k2,p1,p2,k3
+  double fx, fy, cx, cy;
+  int model;           // BEVK_MODEL_*
+  int w, h;            // size of the undistorted (destination) frame
+};
+
+struct Homog { double M[9]; };   // inv(H), as cv2.warpPerspective computes it
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+
+// cvRound / saturate_cast<int>(double): x86 cvtsd2si returns INT_MIN ("integer
+// indefinite") for NaN and out-of-range inputs.
+__device__ __forceinline__ int cv_round(double v) {
+  if (!(fabs(v) < 2147483648.0)) return INT_MIN;
+  return __double2int_rn(v);
+}
+
+// A1 / A11: source-image position (u,v) of undistorted pixel (j,i).
+__device__ __forceinline__ void undistort_point(const CamModel& c, int j, int i, double& u, double& v) {
+  const double dj = (double)j, di = (double)i;
+  const double _x = dadd(dmul(dj, c.iR[0]), dadd(dmul(di, c.iR[1]), c.iR[2]));
+  const double _y = dadd(dmul(dj, c.iR[3]), dadd(dmul(di, c.iR[4]), c.iR[5]));
+  const double _w = dadd(dmul(dj, c.iR[6]), dadd(dmul(di, c.iR[7]), c.iR[8]));
+  if (c.model == 0) {  // equidistant fisheye
+    if (_w <= 0) {
+      const double inf = __longlong_as_double(0x7ff0000000000000LL);
+      u = (_x > 0) ? -inf : inf;
+      v = (_y > 0) ? -inf : inf;
+      return;
+    }
+    const double x = ddiv(_x, _w), y = ddiv(_y, _w);
+    const double r = __dsqrt_rn(dadd(dmul(x, x), dmul(y, y)));
+    const double th = atan(r);
+    const double t2 = dmul(th, th), t4 = dmul(t2, t2), t6 = dmul(t4, t2), t8 = dmul(t4, t4);
+    const double poly = dadd(dadd(dadd(dadd(1.0, dmul(c.k[0], t2)), dmul(c.k[1], t4)), dmul(c.k[2], t6)), dmul(c.k[3], t8));
+    const double thd = dmul(th, poly);
+    const double s = (r == 0) ? 1.0 : ddiv(thd, r);
+    u = dadd(dmul(dmul(c.fx, x), s), c.cx);
+    v = dadd(dmul(dmul(c.fy, y), s), c.cy);
+  } else {             // pinhole, k1 k2 p1 p2 k3
+    const double w = ddiv(1.0, _w), x = dmul(_x, w), y = dmul(_y, w);
+    const double x2 = dmul(x, x), y2 = dmul(y, y);
+    const double r2 = dadd(x2, y2), _2xy = dmul(dmul(2.0, x), y);
+    const double k1 = c.k[0], k2 = c.k[1], p1 = c.k[2], p2 = c.k[3], k3 = c.k[4];
+    const double kr = dadd(1.0, dmul(dadd(dmul(dadd(dmul(k3, r2), k2), r2), k1), r2));
+    const double xd = dadd(dadd(dmul(x, kr), dmul(p1, _2xy)), dmul(p2, dadd(r2, dmul(2.0, x2))));
+    const double yd = dadd(dadd(dmul(y, kr), dmul(p1, dadd(r2, dmul(2.0, y2)))), dmul(p2, _2xy));
+    u = dadd(dmul(c.fx, xd), c.cx);
+    v = dadd(dmul(c.fy, yd), c.cy);
+  }
+}
+
+// CV_16SC2 + CV_16UC1 quantisation of (u,v): map1 = (iu>>5, iv>>5) as int16 (wrapping
+// cast), map2 = (iv&31)*32 + (iu&31).
+__device__ __forceinline__ void quantise_uv(double u, double v, short& mx, short& my, unsigned short& frac) {
+  const int iu = cv_round(dmul(u, (double)TAB));
+  const int iv = cv_round(dmul(v, (double)TAB));
+  mx = (short)(iu >> INTER_BITS);
+  my = (short)(iv >> INTER_BITS);
+  frac = (unsigned short)((iv & (TAB - 1)) * TAB + (iu & (TAB - 1)));
+}
+
+// A3: fixed-point pre-image of destination pixel (x,y) under cv2.warpPerspective.
+// unit = 32 for INTER_LINEAR, 1 for INTER_NEAREST.  OpenCV evaluates in 64-pixel blocks.
+__device__ __forceinline__ void warp_point(const Homog& hm, int x, int y, double unit, int& X, int& Y) {
+  const double* M = hm.M;
+  const int bxi = (x >> 6) << 6;
+  const double bx = (double)bxi, x1 = (double)(x - bxi), dy = (double)y;
+  const double X0 = dadd(dadd(dmul(M[0], bx), dmul(M[1], dy)), M[2]);
+  const double Y0 = dadd(dadd(dmul(M[3], bx), dmul(M[4], dy)), M[5]);
+  const double W0 = dadd(dadd(dmul(M[6], bx), dmul(M[7], dy)), M[8]);
+  double W = dadd(W0, dmul(M[6], x1));
+  W = (W != 0.0) ? ddiv(unit, W) : 0.0;
+  double fX = dmul(dadd(X0, dmul(M[0], x1)), W);
+  double fY = dmul(dadd(Y0, dmul(M[3], x1)), W);
+  fX = fmax(-2147483648.0, fmin(2147483647.0, fX));   // std::max(INT_MIN, std::min(INT_MAX, .))
+  fY = fmax(-2147483648.0, fmin(2147483647.0, fY));
+  X = cv_round(fX);
+  Y = cv_round(fY);
+}
+
+__device__ __forceinline__ int sat_i16(int v) { return max(-32768, min(32767, v)); }
+
+// A2: (sum w*p + 512) >> 10 with integer weights.
+__device__ __forceinline__ int bilerp_q10(int p00, int p01, int p10, int p11, int fx, int fy) {
+  const int w11 = fx * fy, w01 = (fx << 5) - w11, w10 = (fy << 5) - w11;
+  const int w00 = 1024 - (fx << 5) - (fy << 5) + w11;
+  return (w00 * p00 + w01 * p01 + w10 * p10 + w11 * p11 + 512) >> 10;
+}
+
+// ---- A9: OpenCV's 8-bit BGR -> HSV -> (V + delta) -> BGR round trip ------------
+// sdiv[i] = cvRound((255<<12)/i), hdiv[i] = cvRound((180<<12)/(6 i)); filled on the host.
+struct HsvTables { int sdiv[256]; int hdiv[256]; };
+
+__device__ __forceinline__ void hsv_roundtrip(int& b, int& g, int& r, int delta, bool rounding_tail,
+                                              const int* __restrict__ sdiv, const int* __restrict__ hdiv) {
+  const int v = max(b, max(g, r)), mn = min(b, min(g, r));
+  const int d = v - mn;
+  const int s = (d * sdiv[v] + 2048) >> 12;
+  int hh = (v == r) ? (g - b) : ((v == g) ? (b - r + 2 * d) : (r - g + 4 * d));
+  hh = (hh * hdiv[d] + 2048) >> 12;
+  if (hh < 0) hh += 180;
+  const int v2 = max(0, min(255, v + delta));
+  // HSV2BGR, OpenCV's vector body: fp32 with these exact FMA contractions, truncation.
+  const float sf = __fmul_rn((float)s, 1.0f / 255.0f);
+  const float vf = __fmul_rn((float)v2, 1.0f / 255.0f);
+  const float hx = __fmul_rn((float)hh, 6.0f / 180.0f);
+  const float secf = truncf(hx);
+  const float f = __fsub_rn(hx, secf);
+  int sec = (int)secf;
+  sec = sec % 6;
+  const float t0 = vf;
+  const float t1 = __fmul_rn(vf, __fsub_rn(1.0f, sf));
+  const float t2 = __fmul_rn(vf, __fmaf_rn(-sf, f, 1.0f));
+  const float t3 = __fmul_rn(vf, __fmaf_rn(-sf, __fsub_rn(1.0f, f), 1.0f));
+  float fb, fg, fr;
+  switch (sec) {   // sector table {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0}
+    case 0: fb = t1; fg = t3; fr = t0; break;
+    case 1: fb = t1; fg = t0; fr = t2; break;
+    case 2: fb = t3; fg = t0; fr = t1; break;
+    case 3: fb = t0; fg = t2; fr = t1; break;
+    case 4: fb = t0; fg = t1; fr = t3; break;
+    default: fb = t2; fg = t1; fr = t0; break;
+  }
+  fb = __fmul_rn(fb, 255.0f); fg = __fmul_rn(fg, 255.0f); fr = __fmul_rn(fr, 255.0f);
+  if (rounding_tail) {   // the < 32-pixel row tail goes through OpenCV's scalar path, which rounds
+    b = max(0, min(255, __float2int_rn(fb)));
+    g = max(0, min(255, __float2int_rn(fg)));
+    r = max(0, min(255, __float2int_rn(fr)));
+  } else {
+    b = max(0, min(255, (int)fb));
+    g = max(0, min(255, (int)fg));
+    r = max(0, min(255, (int)fr));
+  }
+}
+
+}  // namespace bevk

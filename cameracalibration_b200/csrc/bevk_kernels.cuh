@@ -1,0 +1,613 @@
+// bevk_kernels.cuh -- the sm_100a kernels behind libbevk.so.
+//
+//   k_undistort_map   K1  cv2.fisheye.initUndistortRectifyMap / cv2.initUndistortRectifyMap
+//   k_gather          K3/K4  cv2.remap, fused undistort (no map), cv2.warpPerspective on images
+//   k_warp_maps       K2  cv2.warpPerspective on the 16SC2/16UC1 map planes (BEV LUT build),
+//                         optionally fused with K1 so the full-size undistort map never exists
+//   k_blend_masks     K10 BlendMask.get_blend_mask
+//   k_vsum / k_delta  K8  per-camera sum of V = max(B,G,R) and the luminance offsets
+//   k_bev             K3+K5+K6+K7(+K8 per tap): the fused per-frame kernel
+//   k_gain            K9  grey-world gains + car overlay
+//   k_sat_sum         multi-GPU compose of per-camera partial canvases
+#pragma once
+#include "bevk_device.cuh"
+
+namespace bevk {
+
+constexpr int BEVK_MAX_CAMERAS_K = 8;   // == BEVK_MAX_CAMERAS in include/bevk.h
+
+// ---------------------------------------------------------------------------------
+// K1
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_undistort_map(CamModel cm, short2* __restrict__ map1,
+                                                       unsigned short* __restrict__ map2) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= cm.w || y >= cm.h) return;
+  double u, v;
+  undistort_point(cm, x, y, u, v);
+  short mx, my;
+  unsigned short fr;
+  quantise_uv(u, v, mx, my, fr);
+  const size_t i = (size_t)y * cm.w + x;
+  map1[i] = make_short2(mx, my);
+  map2[i] = fr;
+}
+
+// ---------------------------------------------------------------------------------
+// K3 / K4: generic gather.  MODE 0: maps in HBM, 1: camera model evaluated in-kernel
+// (fused undistort), 2: homography (warpPerspective).
+// ---------------------------------------------------------------------------------
+struct GatherArgs {
+  const uint8_t* src; int sw, sh; long long spitch;
+  uint8_t* dst; int dw, dh; long long dpitch;
+  const short2* map1; const unsigned short* map2;
+  CamModel cm;
+  Homog hm;
+};
+
+template <int C>
+__device__ __forceinline__ void load_px(const uint8_t* __restrict__ src, long long spitch, int sw, int sh,
+                                        int x, int y, int (&p)[C]) {
+  if ((unsigned)x < (unsigned)sw && (unsigned)y < (unsigned)sh) {
+    const uint8_t* q = src + (long long)y * spitch + (long long)x * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c) p[c] = __ldg(q + c);
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) p[c] = 0;
+  }
+}
+
+template <int MODE, int C, int LINEAR>
+__global__ void __launch_bounds__(256) k_gather(GatherArgs a) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= a.dw || y >= a.dh) return;
+  int sx, sy, fx = 0, fy = 0;
+  if (MODE == 2) {
+    int X, Y;
+    if (LINEAR) {
+      warp_point(a.hm, x, y, (double)TAB, X, Y);
+      sx = sat_i16(X >> INTER_BITS); sy = sat_i16(Y >> INTER_BITS);
+      fx = X & (TAB - 1); fy = Y & (TAB - 1);
+    } else {
+      warp_point(a.hm, x, y, 1.0, X, Y);
+      sx = sat_i16(X); sy = sat_i16(Y);
+    }
+  } else {
+    short mx, my;
+    unsigned short fr;
+    bool have_frac = true;
+    if (MODE == 0) {
+      const size_t i = (size_t)y * a.dw + x;
+      const short2 m = a.map1[i];
+      mx = m.x; my = m.y;
+      have_frac = (a.map2 != nullptr);
+      fr = have_frac ? a.map2[i] : 0;
+    } else {
+      double u, v;
+      undistort_point(a.cm, x, y, u, v);
+      quantise_uv(u, v, mx, my, fr);
+    }
+    sx = mx; sy = my;
+    fx = fr & (TAB - 1); fy = (fr >> INTER_BITS) & (TAB - 1);
+    if (!LINEAR && have_frac) {  // OpenCV's NNDeltaTab_i is inverted: frac < 16 picks the +1 neighbour
+      sx += (fx < 16); sy += (fy < 16);
+    }
+  }
+  uint8_t* o = a.dst + (long long)y * a.dpitch + (long long)x * C;
+  if (LINEAR) {
+    int p00[C], p01[C], p10[C], p11[C];
+    load_px<C>(a.src, a.spitch, a.sw, a.sh, sx, sy, p00);
+    load_px<C>(a.src, a.spitch, a.sw, a.sh, sx + 1, sy, p01);
+    load_px<C>(a.src, a.spitch, a.sw, a.sh, sx, sy + 1, p10);
+    load_px<C>(a.src, a.spitch, a.sw, a.sh, sx + 1, sy + 1, p11);
+#pragma unroll
+    for (int c = 0; c < C; ++c) o[c] = (uint8_t)bilerp_q10(p00[c], p01[c], p10[c], p11[c], fx, fy);
+  } else {
+    int p[C];
+    load_px<C>(a.src, a.spitch, a.sw, a.sh, sx, sy, p);
+#pragma unroll
+    for (int c = 0; c < C; ++c) o[c] = (uint8_t)p[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// K2: warpPerspective of the map planes.  FROM_MODEL=1 evaluates the undistort map at
+// the four taps instead of reading und_w x und_h planes from HBM (fused K1+K2).
+// ---------------------------------------------------------------------------------
+struct WarpMapsArgs {
+  const short2* in1; const unsigned short* in2; int sw, sh;   // FROM_MODEL=0
+  CamModel cm;                                                // FROM_MODEL=1 (sw,sh = cm.w,cm.h)
+  Homog hm;
+  short2* out1; unsigned short* out2; int dw, dh;
+};
+
+template <int FROM_MODEL>
+__global__ void __launch_bounds__(256) k_warp_maps(WarpMapsArgs a) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= a.dw || y >= a.dh) return;
+  int X, Y;
+  warp_point(a.hm, x, y, (double)TAB, X, Y);
+  const int sx = sat_i16(X >> INTER_BITS), sy = sat_i16(Y >> INTER_BITS);
+  const float ax = __fmul_rn((float)(X & (TAB - 1)), 1.0f / TAB);
+  const float ay = __fmul_rn((float)(Y & (TAB - 1)), 1.0f / TAB);
+  const float w[4] = {__fmul_rn(__fsub_rn(1.f, ay), __fsub_rn(1.f, ax)), __fmul_rn(__fsub_rn(1.f, ay), ax),
+                      __fmul_rn(ay, __fsub_rn(1.f, ax)), __fmul_rn(ay, ax)};
+  float accx = 0.f, accy = 0.f, accf = 0.f;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int tx = sx + (t & 1), ty = sy + (t >> 1);
+    float vx = 0.f, vy = 0.f, vf = 0.f;
+    if ((unsigned)tx < (unsigned)a.sw && (unsigned)ty < (unsigned)a.sh) {
+      short mx, my;
+      unsigned short fr;
+      if (FROM_MODEL) {
+        double u, v;
+        undistort_point(a.cm, tx, ty, u, v);
+        quantise_uv(u, v, mx, my, fr);
+      } else {
+        const size_t i = (size_t)ty * a.sw + tx;
+        const short2 m = a.in1[i];
+        mx = m.x; my = m.y; fr = a.in2[i];
+      }
+      vx = (float)mx; vy = (float)my; vf = (float)fr;
+    }
+    // acc = ((t0*w0 + t1*w1) + t2*w2) + t3*w3, each product and sum rounded (no FMA)
+    if (t == 0) { accx = __fmul_rn(vx, w[0]); accy = __fmul_rn(vy, w[0]); accf = __fmul_rn(vf, w[0]); }
+    else {
+      accx = __fadd_rn(accx, __fmul_rn(vx, w[t]));
+      accy = __fadd_rn(accy, __fmul_rn(vy, w[t]));
+      accf = __fadd_rn(accf, __fmul_rn(vf, w[t]));
+    }
+  }
+  const size_t o = (size_t)y * a.dw + x;
+  a.out1[o] = make_short2((short)sat_i16(__float2int_rn(accx)), (short)sat_i16(__float2int_rn(accy)));
+  a.out2[o] = (unsigned short)max(0, min(65535, __float2int_rn(accf)));
+}
+
+// ---------------------------------------------------------------------------------
+// K10: blend weights.  polys/out: uint8[4][h][w]; lines: int[8][4] = (ax,ay,bx,by) for
+// FL,FR,BL,BR,LF,LB,RF,RB.
+// ---------------------------------------------------------------------------------
+struct BlendArgs { const uint8_t* polys; uint8_t* out; int w, h; int lines[8][4]; };
+
+__device__ __forceinline__ double seg_dist(double px, double py, const int* L) {
+  const double ax = L[0], ay = L[1], bx = L[2], by = L[3];
+  const double dx = bx - ax, dy = by - ay;
+  const double d1x = px - ax, d1y = py - ay, d2x = px - bx, d2y = py - by;
+  double sq;
+  if (dadd(dmul(d1x, dx), dmul(d1y, dy)) <= 0) sq = dadd(dmul(d1x, d1x), dmul(d1y, d1y));
+  else if (dadd(dmul(d2x, dx), dmul(d2y, dy)) >= 0) sq = dadd(dmul(d2x, d2x), dmul(d2y, d2y));
+  else {
+    const double cr = dadd(dmul(d1y, dx), -dmul(d1x, dy));
+    sq = ddiv(dmul(cr, cr), dadd(dmul(dx, dx), dmul(dy, dy)));
+  }
+  return __dsqrt_rn(sq);
+}
+
+__global__ void __launch_bounds__(256) k_blend_masks(BlendArgs a) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= a.w || y >= a.h) return;
+  const size_t plane = (size_t)a.w * a.h, p = (size_t)y * a.w + x;
+  uint8_t m[4];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) m[n] = a.polys[n * plane + p];
+  // (other, lineA, lineB) per camera, in the reference's order (surroundBEV.py:171-186)
+  const int other[4][2] = {{2, 3}, {2, 3}, {0, 1}, {0, 1}};
+  const int la[4][2] = {{0, 1}, {2, 3}, {4, 5}, {6, 7}};
+  const int lb[4][2] = {{4, 6}, {5, 7}, {0, 2}, {1, 3}};
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    int v = m[n];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (v != 0 && m[other[n][k]] != 0) {
+        const double dA = seg_dist((double)x, (double)y, a.lines[la[n][k]]);
+        const double dB = seg_dist((double)x, (double)y, a.lines[lb[n][k]]);
+        const double a2 = dmul(dA, dA), b2 = dmul(dB, dB);
+        v = (int)dmul(ddiv(a2, dadd(dadd(a2, b2), 1e-6)), 255.0);   // C cast: truncation
+      }
+    }
+    a.out[n * plane + p] = (uint8_t)v;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// K8 part 1: exact integer sum of V = max(B,G,R) over every dense BGR frame.
+// grid = (blocks, n_frames).  48-byte (16-pixel) steps with three 16-byte loads.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned vsum_16px(const uint4 a, const uint4 b, const uint4 c) {
+  const unsigned w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+  unsigned s = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {   // 12 bytes = 4 pixels per 3 words
+    const unsigned w0 = w[3 * q], w1 = w[3 * q + 1], w2 = w[3 * q + 2];
+    // pixel bytes: (w0.0,w0.1,w0.2) (w0.3,w1.0,w1.1) (w1.2,w1.3,w2.0) (w2.1,w2.2,w2.3)
+    s += max(max(w0 & 255u, (w0 >> 8) & 255u), (w0 >> 16) & 255u);
+    s += max(max(w0 >> 24, w1 & 255u), (w1 >> 8) & 255u);
+    s += max(max((w1 >> 16) & 255u, w1 >> 24), w2 & 255u);
+    s += max(max((w2 >> 8) & 255u, (w2 >> 16) & 255u), w2 >> 24);
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(256) k_vsum(const uint8_t* const* __restrict__ frames, long long frame_bytes,
+                                              unsigned long long* __restrict__ vsum) {
+  const uint8_t* f = frames[blockIdx.y];
+  const long long n48 = frame_bytes / 48;
+  unsigned long long acc = 0;
+  if ((reinterpret_cast<uintptr_t>(f) & 15) == 0) {
+    const uint4* f4 = reinterpret_cast<const uint4*>(f);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n48; i += (long long)gridDim.x * blockDim.x) {
+      const uint4 a = __ldg(f4 + 3 * i), b = __ldg(f4 + 3 * i + 1), c = __ldg(f4 + 3 * i + 2);
+      acc += vsum_16px(a, b, c);
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n48 * 16; i += (long long)gridDim.x * blockDim.x) {
+      const uint8_t* q = f + 3 * i;
+      acc += max(max(q[0], q[1]), q[2]);
+    }
+  }
+  if (blockIdx.x == 0)   // tail pixels (frame_bytes % 48)
+    for (long long i = n48 * 16 + threadIdx.x; i * 3 < frame_bytes; i += blockDim.x) {
+      const uint8_t* q = f + 3 * i;
+      acc += max(max(q[0], q[1]), q[2]);
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ unsigned long long part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int k = 0; k < 8; ++k) t += part[k];
+    atomicAdd(vsum + blockIdx.y, t);
+  }
+}
+
+// K8 part 2: delta_c = cvRound(V_mean - V_c) per frame-set (cv2.add rounds the scalar).
+__global__ void k_delta(const unsigned long long* __restrict__ vsum, int n_cam, int batch, double npix,
+                        int* __restrict__ delta) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  double tot = 0.0;
+  for (int c = 0; c < n_cam; ++c) tot = dadd(tot, ddiv((double)vsum[b * n_cam + c], npix));
+  const double vmean = ddiv(tot, (double)n_cam);
+  for (int c = 0; c < n_cam; ++c)
+    delta[b * n_cam + c] = cv_round(dadd(vmean, -ddiv((double)vsum[b * n_cam + c], npix)));
+}
+
+// ---------------------------------------------------------------------------------
+// The fused per-frame kernel.  One CTA = one 32x32 canvas tile of one frame-set.
+// For every camera item of the tile, each thread fetches 4 LUT entries (8 B, coalesced,
+// thread-ordered), gathers the 2x2 taps with aligned 32-bit loads + funnel shifts,
+// interpolates in Q10, applies the blend weight, and saturating-adds into a shared
+// accumulator tile which is finally written to the canvas with 32-bit stores.
+// ---------------------------------------------------------------------------------
+constexpr int TILE = 32;
+constexpr int ACC_PITCH = TILE * 3 + 4;   // 100 B: word aligned, odd word count => no bank conflicts
+
+struct BevParams {
+  const uint8_t* const* srcs;   // device array [batch * n_cam]
+  int n_cam, FW, FH;
+  unsigned pitch;               // source row pitch in bytes (= 3*FW, dense)
+  const int4* tiles;            // x0, y0, first item, item count
+  const int2* items;            // camera, orientation (0: lanes along x, 1: lanes along y)
+  const uint2* lut;             // [item][4][256]
+  uint8_t* out; int BW, BH; long long canvas_bytes;
+  const uint8_t* car;
+  const int* delta;             // [batch * n_cam] luminance offsets (BALANCE)
+  unsigned long long* csum;     // [batch * 3] channel sums of the composed canvas (BALANCE)
+  const int* hsv_tab;           // sdiv[256] ++ hdiv[256]
+  int cam_lo, cam_hi;
+  int tail_start;               // FW - FW % 32: first column of OpenCV's scalar HSV2BGR row tail
+  int wide;                     // 32-bit tap loads allowed (pitch % 4 == 0 and 4-aligned frames)
+};
+
+constexpr unsigned LUT_ACTIVE = 1u << 24, LUT_BORDER = 2u << 24;
+
+template <bool BAL>
+__device__ __forceinline__ void sample_entry(const BevParams& P, const uint8_t* __restrict__ src, const uint2 e,
+                                             int delta, const int* s_tab, int& ob, int& og, int& orr) {
+  const int fx = e.y & 31, fy = (e.y >> 5) & 31;
+  int p[4][3];
+  int sx0 = 0;
+  if (e.y & LUT_BORDER) {
+    const int sx = (short)(e.x & 0xffff), sy = (short)(e.x >> 16);
+    sx0 = sx;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int tx = sx + (t & 1), ty = sy + (t >> 1);
+      if ((unsigned)tx < (unsigned)P.FW && (unsigned)ty < (unsigned)P.FH) {
+        const uint8_t* q = src + (size_t)ty * P.pitch + 3 * tx;
+        p[t][0] = __ldg(q); p[t][1] = __ldg(q + 1); p[t][2] = __ldg(q + 2);
+      } else { p[t][0] = p[t][1] = p[t][2] = 0; }
+    }
+  } else if (P.wide) {
+    const unsigned off = e.x, s8 = (off & 3u) * 8u;
+    const unsigned* q0 = reinterpret_cast<const unsigned*>(src + (off & ~3u));
+    const unsigned* q1 = reinterpret_cast<const unsigned*>(src + (off & ~3u) + P.pitch);
+    const bool third = (s8 == 24u);
+    const unsigned a0 = __ldg(q0), a1 = __ldg(q0 + 1), a2 = third ? __ldg(q0 + 2) : 0u;
+    const unsigned b0 = __ldg(q1), b1 = __ldg(q1 + 1), b2 = third ? __ldg(q1 + 2) : 0u;
+    const unsigned A = __funnelshift_r(a0, a1, s8), A2 = __funnelshift_r(a1, a2, s8);
+    const unsigned B = __funnelshift_r(b0, b1, s8), B2 = __funnelshift_r(b1, b2, s8);
+    p[0][0] = A & 255u; p[0][1] = (A >> 8) & 255u; p[0][2] = (A >> 16) & 255u;
+    p[1][0] = A >> 24;  p[1][1] = A2 & 255u;       p[1][2] = (A2 >> 8) & 255u;
+    p[2][0] = B & 255u; p[2][1] = (B >> 8) & 255u; p[2][2] = (B >> 16) & 255u;
+    p[3][0] = B >> 24;  p[3][1] = B2 & 255u;       p[3][2] = (B2 >> 8) & 255u;
+    if (BAL && P.tail_start != P.FW) sx0 = (off % P.pitch) / 3;
+  } else {
+    const uint8_t* q = src + e.x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      p[0][c] = __ldg(q + c); p[1][c] = __ldg(q + 3 + c);
+      p[2][c] = __ldg(q + P.pitch + c); p[3][c] = __ldg(q + P.pitch + 3 + c);
+    }
+    if (BAL && P.tail_start != P.FW) sx0 = (e.x % P.pitch) / 3;
+  }
+  if (BAL) {
+    // luminance_balance (surroundBEV.py:57-79) applied lazily to the four taps only.
+    // Out-of-frame taps stay 0 (the border constant is not an image pixel).
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      bool inside = true;
+      if (e.y & LUT_BORDER) {
+        const int sx = (short)(e.x & 0xffff), sy = (short)(e.x >> 16);
+        inside = ((unsigned)(sx + (t & 1)) < (unsigned)P.FW) && ((unsigned)(sy + (t >> 1)) < (unsigned)P.FH);
+      }
+      if (inside)
+        hsv_roundtrip(p[t][0], p[t][1], p[t][2], delta, (sx0 + (t & 1)) >= P.tail_start, s_tab, s_tab + 256);
+    }
+  }
+  ob = bilerp_q10(p[0][0], p[1][0], p[2][0], p[3][0], fx, fy);
+  og = bilerp_q10(p[0][1], p[1][1], p[2][1], p[3][1], fx, fy);
+  orr = bilerp_q10(p[0][2], p[1][2], p[2][2], p[3][2], fx, fy);
+  const unsigned w = (e.y >> 16) & 255u;
+  if (w != 255u) {   // BlendMask.__call__: (img * float32(mask/255.0)).astype(uint8)
+    const float wf = __double2float_rn(__ddiv_rn((double)w, 255.0));
+    ob = (int)__fmul_rn((float)ob, wf);
+    og = (int)__fmul_rn((float)og, wf);
+    orr = (int)__fmul_rn((float)orr, wf);
+  }
+}
+
+template <bool BAL>
+__global__ void __launch_bounds__(256) k_bev(BevParams P) {
+  __shared__ __align__(16) uint8_t acc[TILE * ACC_PITCH];
+  __shared__ int s_tab[BAL ? 512 : 1];
+  __shared__ unsigned long long s_sum[BAL ? 3 : 1];
+  const int t = threadIdx.x, lane = t & 31, wrp = t >> 5;
+  const int b = blockIdx.y;
+  const int4 tile = P.tiles[blockIdx.x];
+  for (int i = t; i < TILE * ACC_PITCH / 4; i += 256) reinterpret_cast<unsigned*>(acc)[i] = 0u;
+  if (BAL) {
+    for (int i = t; i < 512; i += 256) s_tab[i] = P.hsv_tab[i];
+    if (t < 3) s_sum[t] = 0ull;
+  }
+  __syncthreads();
+  bool first = true;
+  for (int it = tile.z; it < tile.z + tile.w; ++it) {
+    const int2 item = P.items[it];
+    if (item.x < P.cam_lo || item.x >= P.cam_hi) continue;
+    const uint8_t* __restrict__ src = P.srcs[b * P.n_cam + item.x];
+    const int delta = BAL ? P.delta[b * P.n_cam + item.x] : 0;
+    const uint2* __restrict__ L = P.lut + (size_t)it * (TILE * TILE);
+    uint2 e[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) e[k] = __ldg(L + k * 256 + t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!(e[k].y & LUT_ACTIVE)) continue;
+      int vb, vg, vr;
+      sample_entry<BAL>(P, src, e[k], delta, s_tab, vb, vg, vr);
+      const int major = wrp * 4 + k;
+      const int ax = item.y ? major : lane, ay = item.y ? lane : major;
+      uint8_t* a = acc + ay * ACC_PITCH + ax * 3;
+      if (!first) {   // cv2.add: saturating, camera order front, back, left, right
+        vb = min(255, vb + a[0]); vg = min(255, vg + a[1]); vr = min(255, vr + a[2]);
+      }
+      a[0] = (uint8_t)vb; a[1] = (uint8_t)vg; a[2] = (uint8_t)vr;
+    }
+    first = false;
+    __syncthreads();
+  }
+  // ---- write the tile: thread t -> row t/8, 12 bytes (4 pixels) at byte 12*(t%8) ----
+  const int row = t >> 3, chunk = t & 7;
+  const int gy = tile.y + row, gx = tile.x + chunk * 4;
+  unsigned sb = 0, sg = 0, sr = 0;
+  if (gy < P.BH && gx < P.BW) {
+    const unsigned* a = reinterpret_cast<const unsigned*>(acc + row * ACC_PITCH + chunk * 12);
+    unsigned w0 = a[0], w1 = a[1], w2 = a[2];
+    const size_t o = (size_t)b * P.canvas_bytes + (size_t)gy * P.BW * 3 + (size_t)gx * 3;
+    const bool full = (gx + 4 <= P.BW) && ((P.BW * 3) % 4 == 0) && (P.canvas_bytes % 4 == 0);
+    if (BAL) {   // channel sums of the composed canvas, before gains and car (surroundBEV.py:44-47)
+      const int npx = min(4, P.BW - gx);
+      const unsigned by[12] = {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24, w1 & 255u, (w1 >> 8) & 255u,
+                               (w1 >> 16) & 255u, w1 >> 24, w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < npx) { sb += by[3 * q]; sg += by[3 * q + 1]; sr += by[3 * q + 2]; }
+    }
+    if (full) {
+      if (!BAL && P.car) {
+        const unsigned* c = reinterpret_cast<const unsigned*>(P.car + (size_t)gy * P.BW * 3 + (size_t)gx * 3);
+        w0 = __vaddus4(w0, __ldg(c)); w1 = __vaddus4(w1, __ldg(c + 1)); w2 = __vaddus4(w2, __ldg(c + 2));
+      }
+      unsigned* g = reinterpret_cast<unsigned*>(P.out + o);
+      g[0] = w0; g[1] = w1; g[2] = w2;
+    } else {
+      const int nbytes = min(4, P.BW - gx) * 3;
+      const uint8_t* ab = acc + row * ACC_PITCH + chunk * 12;
+      for (int i = 0; i < nbytes; ++i) {
+        int v = ab[i];
+        if (!BAL && P.car) v = min(255, v + P.car[(size_t)gy * P.BW * 3 + (size_t)gx * 3 + i]);
+        P.out[o + i] = (uint8_t)v;
+      }
+    }
+  }
+  if (BAL) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sb += __shfl_xor_sync(0xffffffffu, sb, o);
+      sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      sr += __shfl_xor_sync(0xffffffffu, sr, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&s_sum[0], (unsigned long long)sb);
+      atomicAdd(&s_sum[1], (unsigned long long)sg);
+      atomicAdd(&s_sum[2], (unsigned long long)sr);
+    }
+    __syncthreads();
+    if (t < 3) atomicAdd(P.csum + b * 3 + t, s_sum[t]);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// K9: color_balance (surroundBEV.py:43-55) + car overlay.  Gains from the channel sums;
+// out = sat(cvRound(double(px) * K_c)) through a 3x256 table built per CTA in shared memory.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gain(uint8_t* __restrict__ canvas, long long canvas_bytes, double npix,
+                                              const unsigned long long* __restrict__ csum,
+                                              const uint8_t* __restrict__ car) {
+  __shared__ uint8_t tab[3][256];
+  const int b = blockIdx.y;
+  {
+    const double B = ddiv((double)csum[b * 3 + 0], npix), G = ddiv((double)csum[b * 3 + 1], npix),
+                 R = ddiv((double)csum[b * 3 + 2], npix);
+    const double K = ddiv(dadd(dadd(R, G), B), 3.0);
+    const double gain[3] = {ddiv(K, B), ddiv(K, G), ddiv(K, R)};
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+      const int c = i >> 8, v = i & 255;
+      const int r = cv_round(dmul((double)v, gain[c]));   // non-finite -> INT_MIN -> saturates to 0, as on x86
+      tab[c][v] = (uint8_t)max(0, min(255, r));
+    }
+  }
+  __syncthreads();
+  uint8_t* cv = canvas + (size_t)b * canvas_bytes;
+  // 12-byte (4-pixel) steps keep the channel phase fixed per byte lane
+  const long long n12 = canvas_bytes / 12;
+  const bool aligned = (canvas_bytes % 4 == 0) && ((reinterpret_cast<uintptr_t>(canvas) & 3) == 0) &&
+                       (!car || (reinterpret_cast<uintptr_t>(car) & 3) == 0);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n12; i += (long long)gridDim.x * blockDim.x) {
+    if (aligned) {
+      unsigned* p = reinterpret_cast<unsigned*>(cv + i * 12);
+      unsigned w[3] = {p[0], p[1], p[2]};
+      unsigned o[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        unsigned r = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int byte_idx = k * 4 + j;
+          r |= (unsigned)tab[byte_idx % 3][(w[k] >> (8 * j)) & 255u] << (8 * j);
+        }
+        o[k] = r;
+      }
+      if (car) {
+        const unsigned* c = reinterpret_cast<const unsigned*>(car + i * 12);
+        o[0] = __vaddus4(o[0], __ldg(c)); o[1] = __vaddus4(o[1], __ldg(c + 1)); o[2] = __vaddus4(o[2], __ldg(c + 2));
+      }
+      p[0] = o[0]; p[1] = o[1]; p[2] = o[2];
+    } else {
+      for (int j = 0; j < 12; ++j) {
+        int v = tab[j % 3][cv[i * 12 + j]];
+        if (car) v = min(255, v + car[i * 12 + j]);
+        cv[i * 12 + j] = (uint8_t)v;
+      }
+    }
+  }
+  if (blockIdx.x == 0)
+    for (long long i = n12 * 12 + threadIdx.x; i < canvas_bytes; i += blockDim.x) {
+      int v = tab[i % 3][cv[i]];
+      if (car) v = min(255, v + car[i]);
+      cv[i] = (uint8_t)v;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Multi-GPU compose: saturating sum of n partial canvases (+ car).  16-byte vectors.
+// ---------------------------------------------------------------------------------
+struct SatSumArgs { const uint8_t* parts[BEVK_MAX_CAMERAS_K]; int n; unsigned long long bytes; const uint8_t* car; uint8_t* out; };
+
+__global__ void __launch_bounds__(256) k_sat_sum(SatSumArgs a) {
+  const unsigned long long n16 = a.bytes / 16;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    uint4 s = __ldg(reinterpret_cast<const uint4*>(a.parts[0]) + i);
+    for (int k = 1; k < a.n; ++k) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.parts[k]) + i);
+      s.x = __vaddus4(s.x, v.x); s.y = __vaddus4(s.y, v.y); s.z = __vaddus4(s.z, v.z); s.w = __vaddus4(s.w, v.w);
+    }
+    if (a.car) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.car) + i);
+      s.x = __vaddus4(s.x, v.x); s.y = __vaddus4(s.y, v.y); s.z = __vaddus4(s.z, v.z); s.w = __vaddus4(s.w, v.w);
+    }
+    reinterpret_cast<uint4*>(a.out)[i] = s;
+  }
+  if (blockIdx.x == 0)
+    for (unsigned long long i = n16 * 16 + threadIdx.x; i < a.bytes; i += blockDim.x) {
+      int s = 0;
+      for (int k = 0; k < a.n; ++k) s = min(255, s + a.parts[k][i]);
+      if (a.car) s = min(255, s + a.car[i]);
+      a.out[i] = (uint8_t)s;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Stand-alone forms of K5/K6 (Mask / BlendMask.__call__), K8 (luminance_balance on whole
+// frames) and the channel sums of K9, for callers that use those reference functions
+// outside BevGenerator.  Dense BGR images.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_apply_mask(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask,
+                                                    uint8_t* __restrict__ out, long long npx, int blend) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned w = mask[i];
+    int b = img[3 * i], g = img[3 * i + 1], r = img[3 * i + 2];
+    if (!blend) { if (!w) b = g = r = 0; }
+    else {
+      const float wf = __double2float_rn(__ddiv_rn((double)w, 255.0));
+      b = (int)__fmul_rn((float)b, wf); g = (int)__fmul_rn((float)g, wf); r = (int)__fmul_rn((float)r, wf);
+    }
+    out[3 * i] = (uint8_t)b; out[3 * i + 1] = (uint8_t)g; out[3 * i + 2] = (uint8_t)r;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_chan_sum(const uint8_t* __restrict__ img, long long npx,
+                                                  unsigned long long* __restrict__ csum) {
+  unsigned long long sb = 0, sg = 0, sr = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+    sb += img[3 * i]; sg += img[3 * i + 1]; sr += img[3 * i + 2];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    sg += __shfl_xor_sync(0xffffffffu, sg, o);
+    sr += __shfl_xor_sync(0xffffffffu, sr, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(csum, sb); atomicAdd(csum + 1, sg); atomicAdd(csum + 2, sr); }
+}
+
+// grid.y = frame index; delta[frame] from k_delta
+__global__ void __launch_bounds__(256) k_lum_apply(const uint8_t* const* __restrict__ frames, uint8_t* const* __restrict__ outs,
+                                                   int w, int h, const int* __restrict__ delta,
+                                                   const int* __restrict__ hsv_tab) {
+  __shared__ int s_tab[512];
+  for (int i = threadIdx.x; i < 512; i += 256) s_tab[i] = hsv_tab[i];
+  __syncthreads();
+  const uint8_t* f = frames[blockIdx.y];
+  uint8_t* o = outs[blockIdx.y];
+  const int d = delta[blockIdx.y], tail = w - (w % 32);
+  const long long npx = (long long)w * h;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+    int b = f[3 * i], g = f[3 * i + 1], r = f[3 * i + 2];
+    hsv_roundtrip(b, g, r, d, (int)(i % w) >= tail, s_tab, s_tab + 256);
+    o[3 * i] = (uint8_t)b; o[3 * i + 1] = (uint8_t)g; o[3 * i + 2] = (uint8_t)r;
+  }
+}
+
+}  // namespace bevk

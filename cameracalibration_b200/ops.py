@@ -1,0 +1,277 @@
+"""NumPy-facing wrappers of the C ABI, one per OpenCV call the reference makes on the
+hot path.  Signatures follow the cv2 functions they replace; all pixel work happens in
+libbevk.so on the GPU."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+INTER_NEAREST, INTER_LINEAR = L.INTER_NEAREST, L.INTER_LINEAR
+
+
+def _interp(flag: int) -> int:
+    if flag not in (INTER_NEAREST, INTER_LINEAR):
+        raise L.BevkError(f"interpolation {flag} is not supported (INTER_NEAREST / INTER_LINEAR only)")
+    return flag
+
+
+def fisheye_init_undistort_rectify_map(K, D, P, size, ctx: L.Context | None = None):
+    """cv2.fisheye.initUndistortRectifyMap(K, D, eye(3), P, size, CV_16SC2)."""
+    return _undistort_map(L.MODEL_FISHEYE, K, D, P, size, ctx)
+
+
+def init_undistort_rectify_map(K, D, P, size, ctx: L.Context | None = None):
+    """cv2.initUndistortRectifyMap(K, D(k1,k2,p1,p2,k3), eye(3), P, size, CV_16SC2)."""
+    return _undistort_map(L.MODEL_PINHOLE, K, D, P, size, ctx)
+
+
+def _undistort_map(model, K, D, P, size, ctx):
+    ctx = ctx or L.default_context()
+    w, h = int(size[0]), int(size[1])
+    d = np.asarray(D, np.float64).reshape(-1)
+    m1 = np.empty((h, w, 2), np.int16)
+    m2 = np.empty((h, w), np.uint16)
+    L.check(ctx.lib.bevk_undistort_map(ctx.h, model, L.dptr(K), L.dptr(d), int(d.size), L.dptr(P), w, h,
+                                       L.vptr(m1), L.vptr(m2)))
+    return m1, m2
+
+
+def remap(src: np.ndarray, map1: np.ndarray, map2: np.ndarray | None, interpolation: int = INTER_LINEAR,
+          ctx: L.Context | None = None) -> np.ndarray:
+    """cv2.remap with CV_16SC2 (+CV_16UC1) maps, BORDER_CONSTANT 0."""
+    ctx = ctx or L.default_context()
+    img, sw, sh, ss, ch = L.image_view(src)
+    m1 = np.ascontiguousarray(map1, np.int16)
+    if m1.ndim != 3 or m1.shape[2] != 2:
+        raise L.BevkError("map1 must be int16[h][w][2] (CV_16SC2)")
+    dh, dw = m1.shape[:2]
+    m2 = None if map2 is None else np.ascontiguousarray(map2, np.uint16)
+    if m2 is not None and m2.shape != (dh, dw):
+        raise L.BevkError("map2 must be uint16[h][w] (CV_16UC1)")
+    out = np.empty((dh, dw) if src.ndim == 2 else (dh, dw, ch), np.uint8)
+    L.check(ctx.lib.bevk_remap(ctx.h, L.vptr(img), sw, sh, ss, ch, L.vptr(m1), None if m2 is None else L.vptr(m2),
+                               dw, dh, L.vptr(out), dw * ch, _interp(interpolation)))
+    return out
+
+
+def warp_perspective(src: np.ndarray, H, dsize, flags: int = INTER_LINEAR, ctx: L.Context | None = None):
+    """cv2.warpPerspective(src, H, dsize, flags) for uint8 images, BORDER_CONSTANT 0."""
+    ctx = ctx or L.default_context()
+    img, sw, sh, ss, ch = L.image_view(src)
+    dw, dh = int(dsize[0]), int(dsize[1])
+    out = np.empty((dh, dw) if src.ndim == 2 else (dh, dw, ch), np.uint8)
+    L.check(ctx.lib.bevk_warp_perspective(ctx.h, L.vptr(img), sw, sh, ss, ch, L.dptr(H), L.vptr(out), dw, dh,
+                                          dw * ch, _interp(flags)))
+    return out
+
+
+def warp_perspective_maps(map1, map2, H, dsize, ctx: L.Context | None = None):
+    """cv2.warpPerspective applied to a CV_16SC2 / CV_16UC1 map pair (Camera.get_bev_maps)."""
+    ctx = ctx or L.default_context()
+    m1 = np.ascontiguousarray(map1, np.int16)
+    m2 = np.ascontiguousarray(map2, np.uint16)
+    sh, sw = m2.shape
+    dw, dh = int(dsize[0]), int(dsize[1])
+    o1 = np.empty((dh, dw, 2), np.int16)
+    o2 = np.empty((dh, dw), np.uint16)
+    L.check(ctx.lib.bevk_warp_maps(ctx.h, L.vptr(m1), L.vptr(m2), sw, sh, L.dptr(H), dw, dh, L.vptr(o1), L.vptr(o2)))
+    return o1, o2
+
+
+def _dense_bgr(img: np.ndarray) -> np.ndarray:
+    if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3:
+        raise L.BevkError("expected a uint8[h][w][3] BGR image")
+    return np.ascontiguousarray(img)
+
+
+def apply_mask(img: np.ndarray, mask: np.ndarray, blend: bool, ctx: L.Context | None = None) -> np.ndarray:
+    """Mask.__call__ (blend=False) / BlendMask.__call__ (blend=True)."""
+    ctx = ctx or L.default_context()
+    a = _dense_bgr(img)
+    m = np.ascontiguousarray(mask, np.uint8)
+    if m.shape != a.shape[:2]:
+        raise L.BevkError("mask and image sizes differ")
+    out = np.empty_like(a)
+    L.check(ctx.lib.bevk_apply_mask(ctx.h, L.vptr(a), L.vptr(m), a.shape[1], a.shape[0], int(blend), L.vptr(out)))
+    return out
+
+
+def color_balance(image: np.ndarray, ctx: L.Context | None = None) -> np.ndarray:
+    ctx = ctx or L.default_context()
+    a = _dense_bgr(image)
+    out = np.empty_like(a)
+    L.check(ctx.lib.bevk_color_balance(ctx.h, L.vptr(a), a.shape[1], a.shape[0], L.vptr(out)))
+    return out
+
+
+def luminance_balance(images, ctx: L.Context | None = None):
+    ctx = ctx or L.default_context()
+    imgs = [_dense_bgr(i) for i in images]
+    if len({i.shape for i in imgs}) != 1:
+        raise L.BevkError("luminance_balance: frames must share one size")
+    outs = [np.empty_like(i) for i in imgs]
+    n = len(imgs)
+    ip = (C.c_void_p * n)(*[i.ctypes.data for i in imgs])
+    op = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+    L.check(ctx.lib.bevk_luminance_balance(ctx.h, ip, n, imgs[0].shape[1], imgs[0].shape[0], op))
+    return outs
+
+
+class Undistorter:
+    """Device-resident undistortion map (or fused camera model) + per-frame gather."""
+    _next_slot = 0
+
+    def __init__(self, K, D, P, size, model: str = "fisheye", fused: bool = False, ctx: L.Context | None = None,
+                 slot: int | None = None):
+        self.ctx = ctx or L.default_context()
+        if slot is None:
+            slot = Undistorter._next_slot % 8
+            Undistorter._next_slot += 1
+        self.slot = slot
+        self.w, self.h = int(size[0]), int(size[1])
+        d = np.asarray(D, np.float64).reshape(-1)
+        m = L.MODEL_FISHEYE if model == "fisheye" else L.MODEL_PINHOLE
+        L.check(self.ctx.lib.bevk_undistorter_set(self.ctx.h, slot, m, L.dptr(K), L.dptr(d), int(d.size), L.dptr(P),
+                                                  self.w, self.h, int(fused)))
+
+    def maps(self):
+        m1 = np.empty((self.h, self.w, 2), np.int16)
+        m2 = np.empty((self.h, self.w), np.uint16)
+        L.check(self.ctx.lib.bevk_undistorter_maps(self.ctx.h, self.slot, L.vptr(m1), L.vptr(m2)))
+        return m1, m2
+
+    def __call__(self, src: np.ndarray, interpolation: int = INTER_LINEAR) -> np.ndarray:
+        img, sw, sh, ss, ch = L.image_view(src)
+        out = np.empty((self.h, self.w) if src.ndim == 2 else (self.h, self.w, ch), np.uint8)
+        L.check(self.ctx.lib.bevk_undistort(self.ctx.h, self.slot, L.vptr(img), sw, sh, ss, ch, L.vptr(out),
+                                            self.w * ch, _interp(interpolation)))
+        return out
+
+
+class BevEngine:
+    """The fused surround-BEV engine (bevk_bev_* entry points)."""
+
+    def __init__(self, n_cam: int, frame_size, bev_size, ctx: L.Context | None = None):
+        self.ctx = ctx or L.Context(L.default_context().device)   # own ctx: the plan is per-ctx state
+        self.n_cam = n_cam
+        self.FW, self.FH = int(frame_size[0]), int(frame_size[1])
+        self.BW, self.BH = int(bev_size[0]), int(bev_size[1])
+        L.check(self.ctx.lib.bevk_bev_configure(self.ctx.h, n_cam, self.FW, self.FH, self.BW, self.BH))
+        self.finalized = False
+
+    def set_camera(self, cam: int, K, D, P, und_size, H):
+        d = np.zeros(4)
+        dd = np.asarray(D, np.float64).reshape(-1)
+        d[:min(4, dd.size)] = dd[:4]
+        L.check(self.ctx.lib.bevk_bev_set_camera(self.ctx.h, cam, L.dptr(K), L.dptr(d), L.dptr(P),
+                                                 int(und_size[0]), int(und_size[1]), L.dptr(H)))
+        self.finalized = False
+
+    def set_maps(self, cam: int, map1, map2):
+        m1 = np.ascontiguousarray(map1, np.int16)
+        m2 = np.ascontiguousarray(map2, np.uint16)
+        if m1.shape != (self.BH, self.BW, 2) or m2.shape != (self.BH, self.BW):
+            raise L.BevkError("BEV maps must match the canvas size")
+        L.check(self.ctx.lib.bevk_bev_set_maps(self.ctx.h, cam, L.vptr(m1), L.vptr(m2)))
+        self.finalized = False
+
+    def get_maps(self, cam: int):
+        m1 = np.empty((self.BH, self.BW, 2), np.int16)
+        m2 = np.empty((self.BH, self.BW), np.uint16)
+        L.check(self.ctx.lib.bevk_bev_get_maps(self.ctx.h, cam, L.vptr(m1), L.vptr(m2)))
+        return m1, m2
+
+    def set_mask(self, cam: int, mask: np.ndarray):
+        m = np.ascontiguousarray(mask, np.uint8)
+        if m.shape != (self.BH, self.BW):
+            raise L.BevkError("mask must be uint8[bev_h][bev_w]")
+        L.check(self.ctx.lib.bevk_bev_set_mask(self.ctx.h, cam, L.vptr(m)))
+        self.finalized = False
+
+    def blend_masks(self, polys: np.ndarray, lines: np.ndarray) -> np.ndarray:
+        p = np.ascontiguousarray(polys, np.uint8)
+        ln = np.ascontiguousarray(lines, np.int32).reshape(8, 4)
+        out = np.empty_like(p)
+        L.check(self.ctx.lib.bevk_blend_masks(self.ctx.h, L.vptr(p), L.vptr(ln), self.BW, self.BH, L.vptr(out)))
+        return out
+
+    def finalize(self):
+        L.check(self.ctx.lib.bevk_bev_finalize(self.ctx.h))
+        self.finalized = True
+
+    def plan_info(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        L.check(self.ctx.lib.bevk_bev_plan_info(self.ctx.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"tiles": a.value, "items": b.value, "lut_bytes": c.value}
+
+    def run(self, frame_sets, car: np.ndarray | None = None, balance: bool = False, out: np.ndarray | None = None):
+        """frame_sets: list (batch) of lists (n_cam) of uint8[FH][FW][3] arrays.  Returns
+        uint8[batch][BH][BW][3]."""
+        if not self.finalized:
+            self.finalize()
+        batch = len(frame_sets)
+        keep, ptrs, stride = [], (C.c_void_p * (batch * self.n_cam))(), None
+        for b, fs in enumerate(frame_sets):
+            if len(fs) != self.n_cam:
+                raise L.BevkError(f"frame-set {b} has {len(fs)} frames, expected {self.n_cam}")
+            for k, f in enumerate(fs):
+                f = self._conform(f)
+                img, w, h, s, ch = L.image_view(f)
+                if stride is None:
+                    stride = s
+                elif s != stride:
+                    img = np.ascontiguousarray(img)
+                    if img.strides[0] != stride:
+                        raise L.BevkError("all frames of a call must share one row stride")
+                keep.append(img)
+                ptrs[b * self.n_cam + k] = img.ctypes.data
+        if out is None:
+            out = np.empty((batch, self.BH, self.BW, 3), np.uint8)
+        carp = None
+        if car is not None:
+            car = np.ascontiguousarray(car, np.uint8)
+            if car.shape != (self.BH, self.BW, 3):
+                raise L.BevkError("car must be uint8[bev_h][bev_w][3]")
+            carp = L.vptr(car)
+        L.check(self.ctx.lib.bevk_bev_run(self.ctx.h, ptrs, stride, batch, carp, L.FLAG_BALANCE if balance else 0,
+                                          L.vptr(out)))
+        return out
+
+    def _conform(self, f: np.ndarray) -> np.ndarray:
+        """The reference never validates frame sizes (cv2.remap samples whatever it is given,
+        zero outside).  The engine's LUT is compiled for FW x FH, so other sizes are embedded
+        into / cropped to an FW x FH zero canvas, which samples identically."""
+        if f.ndim != 3 or f.shape[2] != 3 or f.dtype != np.uint8:
+            raise L.BevkError("frames must be uint8[h][w][3] (BGR)")
+        if f.shape[0] == self.FH and f.shape[1] == self.FW:
+            return f
+        g = np.zeros((self.FH, self.FW, 3), np.uint8)
+        h, w = min(self.FH, f.shape[0]), min(self.FW, f.shape[1])
+        g[:h, :w] = f[:h, :w]
+        return g
+
+    # device-resident entry points (raw device pointers, e.g. torch tensors' data_ptr())
+    def run_device(self, d_srcs_ptr: int, batch: int, d_out_ptr: int, d_car_ptr: int = 0, balance: bool = False):
+        if not self.finalized:
+            self.finalize()
+        L.check(self.ctx.lib.bevk_bev_run_device(self.ctx.h, C.c_void_p(d_srcs_ptr), batch, C.c_void_p(d_car_ptr or None),
+                                                 L.FLAG_BALANCE if balance else 0, C.c_void_p(d_out_ptr)))
+
+    def run_device_cams(self, d_srcs_ptr: int, batch: int, cam_lo: int, cam_hi: int, d_out_ptr: int):
+        if not self.finalized:
+            self.finalize()
+        L.check(self.ctx.lib.bevk_bev_run_device_cams(self.ctx.h, C.c_void_p(d_srcs_ptr), batch, cam_lo, cam_hi,
+                                                      C.c_void_p(d_out_ptr)))
+
+    def sat_sum_device(self, part_ptrs, nbytes: int, d_out_ptr: int, d_car_ptr: int = 0):
+        arr = (C.c_void_p * len(part_ptrs))(*part_ptrs)
+        L.check(self.ctx.lib.bevk_sat_sum_device(self.ctx.h, arr, len(part_ptrs), nbytes, C.c_void_p(d_car_ptr or None),
+                                                 C.c_void_p(d_out_ptr)))
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        L.check(self.ctx.lib.bevk_last_kernel_ms(self.ctx.h, C.byref(ms)))
+        return ms.value

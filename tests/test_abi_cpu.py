@@ -1,0 +1,89 @@
+"""CPU-side checks of the drop-in boundary: libbevk.so loads, exports every symbol that
+include/bevk.h declares, the ctypes table matches the header, and the product refuses to
+run without a GPU instead of falling back to anything."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "bevk.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bevk_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from cameracalibration_b200 import build, _lib
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/bevk.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
+    assert _lib.load().bevk_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from cameracalibration_b200 import _lib
+    with pytest.raises(_lib.BevkError, match="no CPU fallback"):
+        _lib.Context(0)
+    from cameracalibration_b200 import ops
+    import numpy as np
+    with pytest.raises(_lib.BevkError):
+        ops.remap(np.zeros((4, 4, 3), np.uint8), np.zeros((2, 2, 2), np.int16), np.zeros((2, 2), np.uint16))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "cameracalibration_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(d, f)).read()
+                assert "oracle" not in txt.replace("no oracle", ""), f"{f} mentions oracle/"
+
+
+def test_shim_import_leaves_argv_alone_and_keeps_reference_names(monkeypatch):
+    monkeypatch.setattr(sys, "argv", ["prog", "--some-foreign-flag", "-x"])
+    from cameracalibration_b200.SurroundBirdEyeView import surroundBEV as S
+    from cameracalibration_b200.SurroundBirdEyeView import BevGenerator
+    a = BevGenerator.get_args()
+    for k, v in dict(FRAME_WIDTH=1280, FRAME_HEIGHT=1024, BEV_WIDTH=1000, BEV_HEIGHT=1000, CAR_WIDTH=250,
+                     CAR_HEIGHT=400, FOCAL_SCALE=1, SIZE_SCALE=2, BLEND_FLAG=False, BALANCE_FLAG=False).items():
+        assert getattr(a, k) == v
+    for name in ("padding", "color_balance", "luminance_balance", "Camera", "Mask", "BlendMask", "BevGenerator"):
+        assert hasattr(S, name)
+    from cameracalibration_b200.IntrinsicCalibration import InCalibrator
+    from cameracalibration_b200.ExtrinsicCalibration import ExCalibrator
+    assert hasattr(InCalibrator, "undistort") and hasattr(ExCalibrator, "warp")
+    with pytest.raises(Exception, match="camera should be fisheye/normal"):
+        InCalibrator("wide")
+
+
+def test_mask_polygons_match_reference_geometry(fx):
+    """Host-side polygon tables of the shim == the oracle's (which == the reference's)."""
+    from cameracalibration_b200.SurroundBirdEyeView import surroundBEV as S
+    from oracle import restate as R
+    import numpy as np
+    for (BW, BH, CW, CH) in [(1000, 1000, 250, 400), (1200, 1200, 300, 480), (777, 900, 194, 360)]:
+        g = S._Geo()
+        g.BW, g.BH, g.CW, g.CH = BW, BH, CW, CH
+        for n in S.NAMES:
+            assert (S._plain_points(n, g) == R.plain_polygon(n, BW, BH, CW, CH)).all()
+            assert (S._blend_points(n, g) == R.blend_polygon(n, BW, BH, CW, CH)).all()
+        L = R.blend_lines(BW, BH, CW, CH)
+        got = S._seam_lines(g)
+        for i, k in enumerate(["FL", "FR", "BL", "BR", "LF", "LB", "RF", "RB"]):
+            assert (got[i] == L[k]).all()
+    img = np.arange(5 * 7 * 3, dtype=np.uint8).reshape(5, 7, 3)
+    from oracle.cv2_path import padding
+    assert (S.padding(img, 12, 10) == padding(img, 12, 10)).all()
+    assert (S.padding(img, 11, 9) == padding(img, 11, 9)).all()
