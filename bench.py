@@ -166,17 +166,25 @@ def cpu_reference(w, calib, masks, n_sets, repeats, seconds_cap):
                    CW=int(250 * w["BW"] / 1000), CH=int(400 * w["BH"] / 1000))
     ref = C.RefBev(calib, g, w["blend"], w["balance"], masks=[m.copy() for m in masks])
     sets = synthetic_frames(w["FW"], w["FH"], w["n_cam"], n_sets, seed=7)
-    for s in sets[:2]:
-        ref(*s)
-    t0, n = time.perf_counter(), 0
-    for _ in range(repeats):
-        for s in sets:
+    best = None
+    default_threads = cv2.getNumThreads()
+    for threads in sorted({default_threads, os.cpu_count() or default_threads}):   # cv2's default pool and every core
+        cv2.setNumThreads(threads)
+        for s in sets[:2]:
             ref(*s)
-            n += 1
-        if time.perf_counter() - t0 > seconds_cap:
-            break
-    dt = time.perf_counter() - t0
-    return n / dt, cv2.getNumThreads(), f"{n} frame-sets ({n_sets} distinct) of the workload in {dt:.1f} s, cv2 {cv2.__version__} defaults"
+        t0, n = time.perf_counter(), 0
+        for _ in range(repeats):
+            for s in sets:
+                ref(*s)
+                n += 1
+            if time.perf_counter() - t0 > seconds_cap / 2:
+                break
+        dt = time.perf_counter() - t0
+        if best is None or n / dt > best[0]:
+            best = (n / dt, threads, f"{n} frame-sets ({n_sets} distinct) of the workload in {dt:.1f} s, cv2 {cv2.__version__}, "
+                                     f"best of cv2 thread counts {{default {default_threads}, all {os.cpu_count()}}}")
+    cv2.setNumThreads(default_threads)
+    return best
 
 
 # ----------------------------------------------------------------------------- main
@@ -209,6 +217,8 @@ def main():
         g = C.Geometry(FW=w["FW"], FH=w["FH"], BW=w["BW"], BH=w["BH"], CW=250 * w["BW"] // 1000, CH=400 * w["BH"] // 1000)
         masks = [R.blend_mask(n, g.BW, g.BH, g.CW, g.CH) if w["blend"] else C.plain_mask(n, g) for n in NAMES]
         import cv2
+        if os.environ.get("BEVK_REF_THREADS"):
+            cv2.setNumThreads(int(os.environ["BEVK_REF_THREADS"]))
         ref = C.RefBev(calib, g, w["blend"], w["balance"], masks=masks)
         per_step = 4   # bounded sample: 4 of the 32 frame-sets per step
         sets = synthetic_frames(w["FW"], w["FH"], w["n_cam"], per_step, seed=7)
@@ -239,7 +249,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     eng, calib, masks, g = build_engine(w, local)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(device=dev)          # the stream the kernels are launched on (and timed on)
     eng.ctx.set_stream(stream.cuda_stream)
     nb, nc = w["batch"], w["n_cam"]
     host = synthetic_frames(w["FW"], w["FH"], nc, nb, seed=1000 + rank)

@@ -134,7 +134,13 @@ class Context:
             pass
 
     def set_stream(self, stream_ptr: int | None):
-        check(self.lib.bevk_ctx_set_stream(self.h, _p(stream_ptr or 0)))
+        """None -> the ctx's own stream; 0 (torch's default stream handle) -> the legacy
+        default stream (cudaStreamLegacy); anything else -> that cudaStream_t."""
+        if stream_ptr is None:
+            ptr = 0
+        else:
+            ptr = 1 if stream_ptr == 0 else stream_ptr
+        check(self.lib.bevk_ctx_set_stream(self.h, _p(ptr)))
 
     def sync(self):
         check(self.lib.bevk_ctx_sync(self.h))

@@ -24,6 +24,9 @@ struct CamModel {      // cv2.fisheye / cv2 initUndistortRectifyMap inputs, pre-
 
 struct Homog { double M[9]; };   // inv(H), as cv2.warpPerspective computes it
 
+// does undistorted pixel column j take the saturating (vector-body) pack?  (pinhole model only)
+__host__ __device__ __forceinline__ bool pack_saturates(int model, int j, int w) { return model == 1 && j < w - (w % 8); }
+
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
@@ -72,11 +75,15 @@ __device__ __forceinline__ void undistort_point(const CamModel& c, int j, int i,
 
 // CV_16SC2 + CV_16UC1 quantisation of (u,v): map1 = (iu>>5, iv>>5) as int16 (wrapping
 // cast), map2 = (iv&31)*32 + (iu&31).
-__device__ __forceinline__ void quantise_uv(double u, double v, short& mx, short& my, unsigned short& frac) {
+// `saturate`: cv2.initUndistortRectifyMap's (pinhole) vector body packs with signed
+// saturation for columns j < W - W%8; everything else wraps like the C cast it is.
+__device__ __forceinline__ void quantise_uv(double u, double v, short& mx, short& my, unsigned short& frac,
+                                            bool saturate = false) {
   const int iu = cv_round(dmul(u, (double)TAB));
   const int iv = cv_round(dmul(v, (double)TAB));
-  mx = (short)(iu >> INTER_BITS);
-  my = (short)(iv >> INTER_BITS);
+  const int hx = iu >> INTER_BITS, hy = iv >> INTER_BITS;
+  mx = saturate ? (short)max(-32768, min(32767, hx)) : (short)hx;
+  my = saturate ? (short)max(-32768, min(32767, hy)) : (short)hy;
   frac = (unsigned short)((iv & (TAB - 1)) * TAB + (iu & (TAB - 1)));
 }
 

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256) k_undistort_map(CamModel cm, short2* __re
   undistort_point(cm, x, y, u, v);
   short mx, my;
   unsigned short fr;
-  quantise_uv(u, v, mx, my, fr);
+  quantise_uv(u, v, mx, my, fr, pack_saturates(cm.model, x, cm.w));
   const size_t i = (size_t)y * cm.w + x;
   map1[i] = make_short2(mx, my);
   map2[i] = fr;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) k_gather(GatherArgs a) {
     } else {
       double u, v;
       undistort_point(a.cm, x, y, u, v);
-      quantise_uv(u, v, mx, my, fr);
+      quantise_uv(u, v, mx, my, fr, pack_saturates(a.cm.model, x, a.cm.w));
     }
     sx = mx; sy = my;
     fx = fr & (TAB - 1); fy = (fr >> INTER_BITS) & (TAB - 1);
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) k_warp_maps(WarpMapsArgs a) {
       if (FROM_MODEL) {
         double u, v;
         undistort_point(a.cm, tx, ty, u, v);
-        quantise_uv(u, v, mx, my, fr);
+        quantise_uv(u, v, mx, my, fr, pack_saturates(a.cm.model, tx, a.cm.w));
       } else {
         const size_t i = (size_t)ty * a.sw + tx;
         const short2 m = a.in1[i];

@@ -48,14 +48,23 @@ def _ray_terms(iR: np.ndarray, W: int, H: int, running: bool):
             j * iR[2, 0] + (i * iR[2, 1] + iR[2, 2]))
 
 
-def _quantise_maps(u: np.ndarray, v: np.ndarray):
-    """iu=cvRound(u*32) saturated to int32, then split (SURVEY A1 last 2 lines)."""
+def _quantise_maps(u: np.ndarray, v: np.ndarray, simd_saturate: bool = False):
+    """iu=cvRound(u*32) saturated to int32, then split (SURVEY A1 last 2 lines).
+    ``simd_saturate``: cv2.initUndistortRectifyMap's (pinhole) vector body packs map1 with
+    signed saturation for columns j < W - W%8 while its scalar row tail wraps like a C cast
+    (measured against cv2 4.13.0; only visible when |u| or |v| >= 32768 px)."""
     def sat_i32(a):
         a = np.rint(a * TAB)
         a = np.where(np.isnan(a), 0.0, a)
         return np.clip(a, -2147483648.0, 2147483647.0).astype(np.int64)
     iu, iv = sat_i32(u), sat_i32(v)
-    map1 = np.stack([(iu >> INTER_BITS), (iv >> INTER_BITS)], axis=-1).astype(np.int16)
+    mx, my = iu >> INTER_BITS, iv >> INTER_BITS
+    if simd_saturate:
+        W = u.shape[1]
+        body = np.arange(W) < W - W % 8
+        mx = np.where(body, np.clip(mx, -32768, 32767), mx)
+        my = np.where(body, np.clip(my, -32768, 32767), my)
+    map1 = np.stack([mx, my], axis=-1).astype(np.int16)
     map2 = ((iv & (TAB - 1)) * TAB + (iu & (TAB - 1))).astype(np.uint16)
     return map1, map2
 
@@ -106,7 +115,7 @@ def pinhole_map(K, D5, P, W: int, H: int):
     yd = y * kr + p1 * (r2 + 2 * y2) + p2 * _2xy
     u = K[0, 0] * xd + K[0, 2]
     v = K[1, 1] * yd + K[1, 2]
-    return _quantise_maps(u, v)
+    return _quantise_maps(u, v, simd_saturate=True)
 
 
 # ----------------------------------------------------------------------------

@@ -348,12 +348,14 @@ def test_device_resident_and_camera_sharded_compose(ops, fx):
     g = fx.geometry()
     e, _ = _engine(ops, fx, g, blend=True, calib=fx.calib)
     dev = torch.device("cuda", e.ctx.device)
-    e.ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    stream = torch.cuda.Stream(device=dev)
+    e.ctx.set_stream(stream.cuda_stream)
     F = fx.frames()
     d_frames = [torch.from_numpy(f).to(dev) for f in F] * 2
     ptrs = torch.tensor([t.data_ptr() for t in d_frames], dtype=torch.int64, device=dev)
     car = torch.from_numpy(fx.car()).to(dev)
     out = torch.empty((2, 1000, 1000, 3), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
     e.run_device(ptrs.data_ptr(), 2, out.data_ptr(), car.data_ptr(), balance=True)
     torch.cuda.synchronize()
     assert h16(out[1].cpu().numpy()) == fx.gold["native"]["blend1_balance1"]["car"]
