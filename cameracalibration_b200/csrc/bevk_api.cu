@@ -15,6 +15,7 @@
 
 #include "../../include/bevk.h"
 #include "bevk_kernels.cuh"
+#include "bevk_bev.cuh"
 
 using namespace bevk;
 
@@ -128,6 +129,7 @@ struct bevk_ctx {
   bool planned = false;
   long long n_tiles = 0, n_items = 0;
   DevBuf d_tiles, d_items, d_lut, d_hsv;
+  int bev_grid[6] = {0, 0, 0, 0, 0, 0};   // resident CTAs of k_bev<BAL, NB>: index = 3*BAL + {NB=1:0, 4:1, 8:2}
   DevBuf d_frames, d_ptrs, d_canvas, d_car, d_vsum, d_delta, d_csum;
 };
 
@@ -543,7 +545,9 @@ int bevk_bev_finalize(bevk_ctx* c) {
             e.y = frac | (w << 16) | LUT_ACTIVE;
             const bool inside = sx >= 0 && sy >= 0 && sx + 1 < FW && sy + 1 < FH;
             const long long off = (long long)sy * pitch + (long long)sx * 3;
-            if (!inside || off + pitch + 12 > frame_bytes) {
+            // the fast path reads aligned 32-bit words: it needs a 4-byte-multiple pitch and must
+            // not run past the frame; everything else takes the per-tap checked path
+            if (!inside || (pitch & 3u) || off + pitch + 12 > frame_bytes) {
               e.y |= LUT_BORDER;
               e.x = (unsigned)(unsigned short)sx | ((unsigned)(unsigned short)sy << 16);
             } else {
@@ -575,6 +579,18 @@ int bevk_bev_finalize(bevk_ctx* c) {
   RET(c->d_hsv.ensure(512 * sizeof(int)));
   CU(cudaMemcpyAsync(c->d_hsv.p, tab.data(), 512 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  if (c->bev_grid[0] == 0) {   // persistent grid = resident CTAs of each variant
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, c->device));
+    const void* fn[6] = {(const void*)k_bev<false, 1>, (const void*)k_bev<false, 4>, (const void*)k_bev<false, 8>,
+                         (const void*)k_bev<true, 1>, (const void*)k_bev<true, 4>, (const void*)k_bev<true, 8>};
+    const int nb[6] = {1, 4, 8, 1, 4, 8};
+    for (int i = 0; i < 6; ++i) {
+      int per_sm = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn[i], 256, bev_smem_bytes(nb[i])));
+      c->bev_grid[i] = std::max(1, per_sm) * prop.multiProcessorCount;
+    }
+  }
   c->planned = true;
   return BEVK_OK;
 }
@@ -605,7 +621,17 @@ static int run_device(bevk_ctx* c, const void* d_srcs, int batch, const void* d_
   P.hsv_tab = c->d_hsv.as<int>();
   P.cam_lo = cam_lo; P.cam_hi = cam_hi;
   P.tail_start = c->FW - (c->FW % 32);
-  P.wide = (P.pitch % 4 == 0) ? 1 : 0;   // frames from cudaMalloc / torch are >= 256-B aligned
+  P.n_tiles = (int)c->n_tiles; P.batch = batch;
+  // frame-sets per work unit: 4 amortises the LUT decode over a batch; 1 for single frames
+  int nbu = batch >= 4 ? 4 : 1;
+  if (const char* env = getenv("BEVK_NB")) {   // tuning override: 1, 4 or 8
+    const int v = atoi(env);
+    if (v == 1 || v == 4 || v == 8) nbu = v;
+  }
+  const long long units = c->n_tiles * ((batch + nbu - 1) / nbu);
+  const int variant = (bal ? 3 : 0) + (nbu == 8 ? 2 : (nbu == 4 ? 1 : 0));
+  const unsigned bev_blocks = (unsigned)std::max<long long>(1, std::min<long long>(units, c->bev_grid[variant]));
+  const size_t bev_smem = bev_smem_bytes(nbu);
   if (c->timed) CU(cudaEventRecord(c->ev0, c->stream));
   if (bal) {
     const int nf = batch * c->n_cam;
@@ -623,14 +649,18 @@ static int run_device(bevk_ctx* c, const void* d_srcs, int batch, const void* d_
     LAUNCHED(c);
     P.delta = c->d_delta.as<int>();
     P.csum = c->d_csum.as<unsigned long long>();
-    k_bev<true><<<dim3((unsigned)c->n_tiles, batch), 256, 0, c->stream>>>(P);
+    if (nbu == 8) k_bev<true, 8><<<bev_blocks, 256, bev_smem, c->stream>>>(P);
+    else if (nbu == 4) k_bev<true, 4><<<bev_blocks, 256, bev_smem, c->stream>>>(P);
+    else k_bev<true, 1><<<bev_blocks, 256, bev_smem, c->stream>>>(P);
     LAUNCHED(c);
     const int gblocks = (int)std::max<long long>(1, std::min<long long>(P.canvas_bytes / (12 * 256) + 1, 148 * 8 / std::max(1, std::min(batch, 64)) + 1));
     k_gain<<<dim3(gblocks, batch), 256, 0, c->stream>>>(P.out, P.canvas_bytes, (double)c->BW * (double)c->BH,
                                                         c->d_csum.as<unsigned long long>(), P.car);
     LAUNCHED(c);
   } else {
-    k_bev<false><<<dim3((unsigned)c->n_tiles, batch), 256, 0, c->stream>>>(P);
+    if (nbu == 8) k_bev<false, 8><<<bev_blocks, 256, bev_smem, c->stream>>>(P);
+    else if (nbu == 4) k_bev<false, 4><<<bev_blocks, 256, bev_smem, c->stream>>>(P);
+    else k_bev<false, 1><<<bev_blocks, 256, bev_smem, c->stream>>>(P);
     LAUNCHED(c);
   }
   if (c->timed) CU(cudaEventRecord(c->ev1, c->stream));

@@ -282,192 +282,6 @@ __global__ void k_delta(const unsigned long long* __restrict__ vsum, int n_cam, 
 }
 
 // ---------------------------------------------------------------------------------
-// The fused per-frame kernel.  One CTA = one 32x32 canvas tile of one frame-set.
-// For every camera item of the tile, each thread fetches 4 LUT entries (8 B, coalesced,
-// thread-ordered), gathers the 2x2 taps with aligned 32-bit loads + funnel shifts,
-// interpolates in Q10, applies the blend weight, and saturating-adds into a shared
-// accumulator tile which is finally written to the canvas with 32-bit stores.
-// ---------------------------------------------------------------------------------
-constexpr int TILE = 32;
-constexpr int ACC_PITCH = TILE * 3 + 4;   // 100 B: word aligned, odd word count => no bank conflicts
-
-struct BevParams {
-  const uint8_t* const* srcs;   // device array [batch * n_cam]
-  int n_cam, FW, FH;
-  unsigned pitch;               // source row pitch in bytes (= 3*FW, dense)
-  const int4* tiles;            // x0, y0, first item, item count
-  const int2* items;            // camera, orientation (0: lanes along x, 1: lanes along y)
-  const uint2* lut;             // [item][4][256]
-  uint8_t* out; int BW, BH; long long canvas_bytes;
-  const uint8_t* car;
-  const int* delta;             // [batch * n_cam] luminance offsets (BALANCE)
-  unsigned long long* csum;     // [batch * 3] channel sums of the composed canvas (BALANCE)
-  const int* hsv_tab;           // sdiv[256] ++ hdiv[256]
-  int cam_lo, cam_hi;
-  int tail_start;               // FW - FW % 32: first column of OpenCV's scalar HSV2BGR row tail
-  int wide;                     // 32-bit tap loads allowed (pitch % 4 == 0 and 4-aligned frames)
-};
-
-constexpr unsigned LUT_ACTIVE = 1u << 24, LUT_BORDER = 2u << 24;
-
-template <bool BAL>
-__device__ __forceinline__ void sample_entry(const BevParams& P, const uint8_t* __restrict__ src, const uint2 e,
-                                             int delta, const int* s_tab, int& ob, int& og, int& orr) {
-  const int fx = e.y & 31, fy = (e.y >> 5) & 31;
-  int p[4][3];
-  int sx0 = 0;
-  if (e.y & LUT_BORDER) {
-    const int sx = (short)(e.x & 0xffff), sy = (short)(e.x >> 16);
-    sx0 = sx;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int tx = sx + (t & 1), ty = sy + (t >> 1);
-      if ((unsigned)tx < (unsigned)P.FW && (unsigned)ty < (unsigned)P.FH) {
-        const uint8_t* q = src + (size_t)ty * P.pitch + 3 * tx;
-        p[t][0] = __ldg(q); p[t][1] = __ldg(q + 1); p[t][2] = __ldg(q + 2);
-      } else { p[t][0] = p[t][1] = p[t][2] = 0; }
-    }
-  } else if (P.wide) {
-    const unsigned off = e.x, s8 = (off & 3u) * 8u;
-    const unsigned* q0 = reinterpret_cast<const unsigned*>(src + (off & ~3u));
-    const unsigned* q1 = reinterpret_cast<const unsigned*>(src + (off & ~3u) + P.pitch);
-    const bool third = (s8 == 24u);
-    const unsigned a0 = __ldg(q0), a1 = __ldg(q0 + 1), a2 = third ? __ldg(q0 + 2) : 0u;
-    const unsigned b0 = __ldg(q1), b1 = __ldg(q1 + 1), b2 = third ? __ldg(q1 + 2) : 0u;
-    const unsigned A = __funnelshift_r(a0, a1, s8), A2 = __funnelshift_r(a1, a2, s8);
-    const unsigned B = __funnelshift_r(b0, b1, s8), B2 = __funnelshift_r(b1, b2, s8);
-    p[0][0] = A & 255u; p[0][1] = (A >> 8) & 255u; p[0][2] = (A >> 16) & 255u;
-    p[1][0] = A >> 24;  p[1][1] = A2 & 255u;       p[1][2] = (A2 >> 8) & 255u;
-    p[2][0] = B & 255u; p[2][1] = (B >> 8) & 255u; p[2][2] = (B >> 16) & 255u;
-    p[3][0] = B >> 24;  p[3][1] = B2 & 255u;       p[3][2] = (B2 >> 8) & 255u;
-    if (BAL && P.tail_start != P.FW) sx0 = (off % P.pitch) / 3;
-  } else {
-    const uint8_t* q = src + e.x;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      p[0][c] = __ldg(q + c); p[1][c] = __ldg(q + 3 + c);
-      p[2][c] = __ldg(q + P.pitch + c); p[3][c] = __ldg(q + P.pitch + 3 + c);
-    }
-    if (BAL && P.tail_start != P.FW) sx0 = (e.x % P.pitch) / 3;
-  }
-  if (BAL) {
-    // luminance_balance (surroundBEV.py:57-79) applied lazily to the four taps only.
-    // Out-of-frame taps stay 0 (the border constant is not an image pixel).
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      bool inside = true;
-      if (e.y & LUT_BORDER) {
-        const int sx = (short)(e.x & 0xffff), sy = (short)(e.x >> 16);
-        inside = ((unsigned)(sx + (t & 1)) < (unsigned)P.FW) && ((unsigned)(sy + (t >> 1)) < (unsigned)P.FH);
-      }
-      if (inside)
-        hsv_roundtrip(p[t][0], p[t][1], p[t][2], delta, (sx0 + (t & 1)) >= P.tail_start, s_tab, s_tab + 256);
-    }
-  }
-  ob = bilerp_q10(p[0][0], p[1][0], p[2][0], p[3][0], fx, fy);
-  og = bilerp_q10(p[0][1], p[1][1], p[2][1], p[3][1], fx, fy);
-  orr = bilerp_q10(p[0][2], p[1][2], p[2][2], p[3][2], fx, fy);
-  const unsigned w = (e.y >> 16) & 255u;
-  if (w != 255u) {   // BlendMask.__call__: (img * float32(mask/255.0)).astype(uint8)
-    const float wf = __double2float_rn(__ddiv_rn((double)w, 255.0));
-    ob = (int)__fmul_rn((float)ob, wf);
-    og = (int)__fmul_rn((float)og, wf);
-    orr = (int)__fmul_rn((float)orr, wf);
-  }
-}
-
-template <bool BAL>
-__global__ void __launch_bounds__(256) k_bev(BevParams P) {
-  __shared__ __align__(16) uint8_t acc[TILE * ACC_PITCH];
-  __shared__ int s_tab[BAL ? 512 : 1];
-  __shared__ unsigned long long s_sum[BAL ? 3 : 1];
-  const int t = threadIdx.x, lane = t & 31, wrp = t >> 5;
-  const int b = blockIdx.y;
-  const int4 tile = P.tiles[blockIdx.x];
-  for (int i = t; i < TILE * ACC_PITCH / 4; i += 256) reinterpret_cast<unsigned*>(acc)[i] = 0u;
-  if (BAL) {
-    for (int i = t; i < 512; i += 256) s_tab[i] = P.hsv_tab[i];
-    if (t < 3) s_sum[t] = 0ull;
-  }
-  __syncthreads();
-  bool first = true;
-  for (int it = tile.z; it < tile.z + tile.w; ++it) {
-    const int2 item = P.items[it];
-    if (item.x < P.cam_lo || item.x >= P.cam_hi) continue;
-    const uint8_t* __restrict__ src = P.srcs[b * P.n_cam + item.x];
-    const int delta = BAL ? P.delta[b * P.n_cam + item.x] : 0;
-    const uint2* __restrict__ L = P.lut + (size_t)it * (TILE * TILE);
-    uint2 e[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) e[k] = __ldg(L + k * 256 + t);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (!(e[k].y & LUT_ACTIVE)) continue;
-      int vb, vg, vr;
-      sample_entry<BAL>(P, src, e[k], delta, s_tab, vb, vg, vr);
-      const int major = wrp * 4 + k;
-      const int ax = item.y ? major : lane, ay = item.y ? lane : major;
-      uint8_t* a = acc + ay * ACC_PITCH + ax * 3;
-      if (!first) {   // cv2.add: saturating, camera order front, back, left, right
-        vb = min(255, vb + a[0]); vg = min(255, vg + a[1]); vr = min(255, vr + a[2]);
-      }
-      a[0] = (uint8_t)vb; a[1] = (uint8_t)vg; a[2] = (uint8_t)vr;
-    }
-    first = false;
-    __syncthreads();
-  }
-  // ---- write the tile: thread t -> row t/8, 12 bytes (4 pixels) at byte 12*(t%8) ----
-  const int row = t >> 3, chunk = t & 7;
-  const int gy = tile.y + row, gx = tile.x + chunk * 4;
-  unsigned sb = 0, sg = 0, sr = 0;
-  if (gy < P.BH && gx < P.BW) {
-    const unsigned* a = reinterpret_cast<const unsigned*>(acc + row * ACC_PITCH + chunk * 12);
-    unsigned w0 = a[0], w1 = a[1], w2 = a[2];
-    const size_t o = (size_t)b * P.canvas_bytes + (size_t)gy * P.BW * 3 + (size_t)gx * 3;
-    const bool full = (gx + 4 <= P.BW) && ((P.BW * 3) % 4 == 0) && (P.canvas_bytes % 4 == 0);
-    if (BAL) {   // channel sums of the composed canvas, before gains and car (surroundBEV.py:44-47)
-      const int npx = min(4, P.BW - gx);
-      const unsigned by[12] = {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24, w1 & 255u, (w1 >> 8) & 255u,
-                               (w1 >> 16) & 255u, w1 >> 24, w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24};
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (q < npx) { sb += by[3 * q]; sg += by[3 * q + 1]; sr += by[3 * q + 2]; }
-    }
-    if (full) {
-      if (!BAL && P.car) {
-        const unsigned* c = reinterpret_cast<const unsigned*>(P.car + (size_t)gy * P.BW * 3 + (size_t)gx * 3);
-        w0 = __vaddus4(w0, __ldg(c)); w1 = __vaddus4(w1, __ldg(c + 1)); w2 = __vaddus4(w2, __ldg(c + 2));
-      }
-      unsigned* g = reinterpret_cast<unsigned*>(P.out + o);
-      g[0] = w0; g[1] = w1; g[2] = w2;
-    } else {
-      const int nbytes = min(4, P.BW - gx) * 3;
-      const uint8_t* ab = acc + row * ACC_PITCH + chunk * 12;
-      for (int i = 0; i < nbytes; ++i) {
-        int v = ab[i];
-        if (!BAL && P.car) v = min(255, v + P.car[(size_t)gy * P.BW * 3 + (size_t)gx * 3 + i]);
-        P.out[o + i] = (uint8_t)v;
-      }
-    }
-  }
-  if (BAL) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      sb += __shfl_xor_sync(0xffffffffu, sb, o);
-      sg += __shfl_xor_sync(0xffffffffu, sg, o);
-      sr += __shfl_xor_sync(0xffffffffu, sr, o);
-    }
-    if (lane == 0) {
-      atomicAdd(&s_sum[0], (unsigned long long)sb);
-      atomicAdd(&s_sum[1], (unsigned long long)sg);
-      atomicAdd(&s_sum[2], (unsigned long long)sr);
-    }
-    __syncthreads();
-    if (t < 3) atomicAdd(P.csum + b * 3 + t, s_sum[t]);
-  }
-}
-
-// ---------------------------------------------------------------------------------
 // K9: color_balance (surroundBEV.py:43-55) + car overlay.  Gains from the channel sums;
 // out = sat(cvRound(double(px) * K_c)) through a 3x256 table built per CTA in shared memory.
 // ---------------------------------------------------------------------------------

@@ -384,3 +384,22 @@ def test_errors_are_loud(ops, fx):
         ops.remap(np.zeros((4, 4, 2), np.uint8), np.zeros((2, 2, 2), np.int16), np.zeros((2, 2), np.uint16))
     with pytest.raises(BevkError, match="out of range"):
         ops.BevEngine(9, (64, 48), (40, 40))
+
+
+def test_blend_weight_all_pixel_mask_pairs(ops):
+    """Every (pixel value, mask value) pair through the fused kernel: identity LUT, image
+    value = column, mask = row."""
+    n = 256
+    e = ops.BevEngine(1, (n + 2, n + 2), (n, n))
+    yy, xx = np.mgrid[0:n, 0:n]
+    e.set_maps(0, np.stack([xx, yy], -1).astype(np.int16), np.zeros((n, n), np.uint16))
+    mask = yy.astype(np.uint8)
+    e.set_mask(0, mask)
+    img = np.zeros((n + 2, n + 2, 3), np.uint8)
+    img[:n, :n, 0] = xx
+    img[:n, :n, 1] = 255 - xx
+    img[:n, :n, 2] = (xx * 7) & 255
+    got = e.run([[img]])[0]
+    want = R.apply_blend(img[:n, :n], mask)
+    assert (got == want).all()
+    assert (ops.apply_mask(img[:n, :n], mask, blend=True) == want).all()

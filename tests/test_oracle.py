@@ -148,3 +148,14 @@ def test_live_unmodified_reference(fx):
     assert h16(b(*F, fx.car())) == fx.gold["native"]["blend1_balance1"]["car"]
     for n, cam in zip(NAMES, b.cameras):
         assert h16(cam.bev_maps[0]) == fx.gold["camera"][n]["bev_map1"]
+
+
+def test_blend_weight_integer_identity_exhaustive():
+    """The kernel's integer blend weighting == BlendMask.__call__'s float expression
+    (surroundBEV.py:279-280) for every (pixel, mask) pair."""
+    px = np.arange(256, dtype=np.uint8)[None, :].repeat(256, 0)
+    mask = np.arange(256, dtype=np.uint8)[:, None].repeat(256, 1)
+    ref = (px[..., None] * (np.repeat(mask[:, :, None], 1, axis=2) / 255.0).astype(np.float32)).astype(np.uint8)[..., 0]
+    wm = mask.astype(np.int64) * 257 + (mask != 0)
+    assert ((px.astype(np.int64) * wm) >> 16 == ref).all()
+    assert (R.apply_blend(np.stack([px] * 3, -1), mask)[..., 0] == ref).all()
