@@ -197,6 +197,9 @@ def main():
     ap.add_argument("--batch", type=int, default=WORKLOAD["batch"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (default: min(steps, 20))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="frames", choices=["frames", "cameras"],
+                    help="multi-GPU policy: frame-sets per GPU (weak scaling, no collective; default) or cameras per GPU "
+                         "(strong scaling over one batch, one NCCL all-gather of partial canvases per step)")
     a = ap.parse_args()
     w = dict(WORKLOAD, batch=a.batch)
     rank = int(os.environ.get("RANK", "0"))
@@ -205,7 +208,8 @@ def main():
     metric, unit = "surround_bev_frame_sets_per_sec", "frame-sets/s"
     config = {"workload": f"{w['batch']} frame-sets/GPU x 4 cams {w['FW']}x{w['FH']} BGR -> {w['BW']}x{w['BH']} BEV, "
                           f"blend={w['blend']} balance={w['balance']} (BASELINE configs[3] shape)",
-              "sharding": "frame-sets per GPU, no data-path collective",
+              "sharding": ("frame-sets per GPU, no data-path collective" if a.shard == "frames" else
+                           "cameras per GPU, one NCCL all-gather of partial canvases per step + local saturating-sum compose"),
               "l2": "inputs (796 MB/step) larger than L2; frame-invariant LUT (8 MB) stays L2-resident by design"}
 
     if a.impl == "reference":
@@ -252,14 +256,20 @@ def main():
     stream = torch.cuda.Stream(device=dev)          # the stream the kernels are launched on (and timed on)
     eng.ctx.set_stream(stream.cuda_stream)
     nb, nc = w["batch"], w["n_cam"]
-    host = synthetic_frames(w["FW"], w["FH"], nc, nb, seed=1000 + rank)
+    # frames policy: every rank has its own batch; cameras policy: all ranks work on the same batch
+    host = synthetic_frames(w["FW"], w["FH"], nc, nb, seed=1000 + (rank if a.shard == "frames" else 0))
     d_frames = torch.from_numpy(host).to(dev)                       # [batch][cam][FH][FW][3], resident in HBM
     fbytes = w["FW"] * w["FH"] * 3
     ptrs = torch.tensor([d_frames.data_ptr() + i * fbytes for i in range(nb * nc)], dtype=torch.int64, device=dev)
     d_out = torch.empty((nb, w["BH"], w["BW"], 3), dtype=torch.uint8, device=dev)
 
+    from cameracalibration_b200.sharding import ShardedBev
+    sharded = ShardedBev(eng, a.shard if world > 1 else "frames")
+    cams = a.shard == "cameras" and world > 1
+
     def step():
-        eng.run_device(ptrs.data_ptr(), nb, d_out.data_ptr(), 0, balance=w["balance"])
+        with torch.cuda.stream(stream):   # NCCL orders itself against torch's current stream
+            sharded.render(ptrs, nb, d_out, None, balance=w["balance"])
 
     def barrier():
         if world > 1:
@@ -291,7 +301,7 @@ def main():
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_all = float(tmax.item())
-    value = world * nb * a.steps / (ms_all / 1e3)
+    value = (nb if cams else world * nb) * a.steps / (ms_all / 1e3)
 
     # ---- kernel-only time of k_bev via the ctx's own events (single launch, averaged) ----
     kt = []
@@ -319,7 +329,7 @@ def main():
     te = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * nb * n_e2e / float(te.item())
+    e2e_value = world * nb * n_e2e / float(te.item())   # e2e always runs the frames policy (each rank its own batch)
     same = bool((torch.from_numpy(np.asarray(pin_out)).to(dev) == d_out).all().item())
 
     if rank == 0:
@@ -331,16 +341,26 @@ def main():
         peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback")
         src_b, canvas_b = algorithmic_bytes(eng, masks, w)
         alg = (src_b + canvas_b) * nb
-        achieved = alg / (k_ms / 1e3) / 1e9
+        # one step == one k_bev launch: its average duration over the timed region is ms/step (events on the launch stream)
+        launch_ms = ms / a.steps
+        achieved = alg / (launch_ms / 1e3) / 1e9
+        traffic = None
+        try:   # per-launch DRAM bytes of the same kernel/workload from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "k_bev_traffic.json")))
+            if tj.get("workload_batch") == nb and not cams:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except Exception:
+            pass
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
-                "ms_per_step": ms_all / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_all / a.steps, "higher_is_better": True, "scaling": "strong" if cams else "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic", "config": config,
                 "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": nb * nc * fbytes,
                         "d2h_bytes_per_step": nb * w["BW"] * w["BH"] * 3, "steps": n_e2e,
                         "api": "BevEngine.run (ctypes -> bevk_bev_run), pinned host frames", "matches_device_path": same},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "k_bev<false>", "kernel_ms": k_ms, "peak_source": peak_src,
+                             "traffic": traffic, "kernel": "k_bev<false,4>", "kernel_ms": launch_ms,
+                             "kernel_ms_isolated": k_ms, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg,
                              "algorithmic_bytes_per_frame_set": {"source_unique_32B_sectors": src_b, "canvas_write": canvas_b}},
                 "clocks": sampler.summary(), "plan": eng.plan_info()}
