@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -127,7 +128,7 @@ struct bevk_ctx {
   int n_cam = 0, FW = 0, FH = 0, BW = 0, BH = 0;
   BevCam cam[BEVK_MAX_CAMERAS];
   bool planned = false;
-  long long n_tiles = 0, n_items = 0;
+  long long n_tiles = 0, n_items = 0, staged_items = 0, staged_bytes = 0;
   DevBuf d_tiles, d_items, d_lut, d_hsv;
   int bev_grid[6] = {0, 0, 0, 0, 0, 0};   // resident CTAs of k_bev<BAL, NB>: index = 3*BAL + {NB=1:0, 4:1, 8:2}
   DevBuf d_frames, d_ptrs, d_canvas, d_car, d_vsum, d_delta, d_csum;
@@ -507,9 +508,10 @@ int bevk_bev_finalize(bevk_ctx* c) {
   const long long frame_bytes = (long long)pitch * FH;
   const int tx = (BW + TILE - 1) / TILE, ty = (BH + TILE - 1) / TILE;
   std::vector<int4> tiles;
-  std::vector<int2> items;
-  std::vector<uint2> lut;
+  std::vector<BevItem> items;
+  std::vector<uint4> lut;
   tiles.reserve((size_t)tx * ty);
+  c->staged_items = 0; c->staged_bytes = 0;
   for (int tj = 0; tj < ty; ++tj)
     for (int ti = 0; ti < tx; ++ti) {
       const int x0 = ti * TILE, y0 = tj * TILE;
@@ -518,44 +520,77 @@ int bevk_bev_finalize(bevk_ctx* c) {
         const uint8_t* mk = c->cam[k].mask.data();
         bool any = false;
         long long cx = 0, cy = 0;   // source-row changes along canvas x vs canvas y
+        // source bounding box of the in-frame taps of this (tile, camera): rows [by0, by1), bytes [bx0, bx1)
+        int by0 = INT_MAX, by1 = -1, bx0 = INT_MAX, bx1 = -1;
+        auto in_frame = [&](int sx, int sy) {
+          const long long off = (long long)sy * pitch + (long long)sx * 3;
+          return sx >= 0 && sy >= 0 && sx + 1 < FW && sy + 1 < FH && !(pitch & 3u) && off + pitch + 12 <= frame_bytes;
+        };
         for (int y = y0; y < std::min(y0 + TILE, BH); ++y)
           for (int x = x0; x < std::min(x0 + TILE, BW); ++x) {
             const size_t p = (size_t)y * BW + x;
             if (!mk[p]) continue;
             any = true;
-            const int sy = m1[k][2 * p + 1];
+            const int sx = m1[k][2 * p], sy = m1[k][2 * p + 1];
             if (x + 1 < BW && mk[p + 1]) cx += std::abs(m1[k][2 * (p + 1) + 1] - sy);
             if (y + 1 < BH && mk[p + BW]) cy += std::abs(m1[k][2 * (p + BW) + 1] - sy);
+            if (in_frame(sx, sy)) {
+              const int wl = (3 * sx) & ~3;   // first word the fast path reads; it may read 12 bytes from there
+              by0 = std::min(by0, sy); by1 = std::max(by1, sy + 2);
+              bx0 = std::min(bx0, wl); bx1 = std::max(bx1, wl + 12);
+            }
           }
         if (!any) continue;
-        const int orient = cy < cx ? 1 : 0;
+        BevItem item{};
+        item.cam = k;
+        item.orient = cy < cx ? 1 : 0;
+        // Source-box staging in shared memory is disabled: measured slower than the batched global
+        // gather in round 1 (experiments/).  The box statistics are still
+        // collected for bevk_bev_stage_info; no LUT entry is made box-relative.
+        const bool use_staging = false;
+        if (by1 > by0 && (pitch % 16u) == 0) {
+          int xa = bx0 & ~15, xb = (bx1 + 15) & ~15;
+          if (xb > (int)pitch) { xa -= xb - (int)pitch; xb = (int)pitch; }   // pitch % 16 == 0 keeps xa aligned
+          xa = std::max(xa, 0);
+          const long long bytes = (long long)(by1 - by0) * (xb - xa);
+          if (bytes <= 12288) {
+            item.staged = use_staging ? 1 : 0;
+            item.src_off = (unsigned)((long long)by0 * pitch + xa);
+            item.rows = by1 - by0; item.row_bytes = xb - xa;
+            item.pad0 = by0; item.pad1 = xa;
+            c->staged_items++; c->staged_bytes += bytes;
+          }
+        }
         const size_t base = lut.size();
-        lut.resize(base + TILE * TILE, make_uint2(0u, 0u));
+        lut.resize(base + TILE * TILE, make_uint4(0u, 0u, 0u, 0u));
         for (int kk = 0; kk < 4; ++kk)
           for (int th = 0; th < 256; ++th) {
             const int lane = th & 31, major = (th >> 5) * 4 + kk;
-            const int x = x0 + (orient ? major : lane), y = y0 + (orient ? lane : major);
+            const int x = x0 + (item.orient ? major : lane), y = y0 + (item.orient ? lane : major);
             if (x >= BW || y >= BH) continue;
             const size_t p = (size_t)y * BW + x;
             const unsigned w = mk[p];
             if (!w) continue;
             const int sx = m1[k][2 * p], sy = m1[k][2 * p + 1];
-            const unsigned frac = m2[k][p] & 1023u;
-            uint2 e;
-            e.y = frac | (w << 16) | LUT_ACTIVE;
-            const bool inside = sx >= 0 && sy >= 0 && sx + 1 < FW && sy + 1 < FH;
-            const long long off = (long long)sy * pitch + (long long)sx * 3;
-            // the fast path reads aligned 32-bit words: it needs a 4-byte-multiple pitch and must
-            // not run past the frame; everything else takes the per-tap checked path
-            if (!inside || (pitch & 3u) || off + pitch + 12 > frame_bytes) {
-              e.y |= LUT_BORDER;
+            const unsigned frac = m2[k][p] & 1023u, fx = frac & 31u, fy = frac >> 5;
+            const unsigned w11 = fx * fy, w01 = (fx << 5) - w11, w10 = (fy << 5) - w11, w00 = 1024u - (fx << 5) - (fy << 5) + w11;
+            uint4 e;
+            e.y = w00 | (w01 << 16);                       // DP2A weight pairs, top / bottom source row
+            e.z = w10 | (w11 << 16);
+            e.w = (w * 257u + 1u) | (frac << 17) | LUT_ACTIVE;   // blend multiplier (w > 0 here), fraction, flags
+            if (!in_frame(sx, sy)) {
+              // out-of-frame taps, a pitch that is not a multiple of 4, or the very end of the frame:
+              // per-tap checked path
+              e.w |= LUT_BORDER;
               e.x = (unsigned)(unsigned short)sx | ((unsigned)(unsigned short)sy << 16);
+            } else if (item.staged) {
+              e.x = (unsigned)((sy - item.pad0) * item.row_bytes + (3 * sx - item.pad1));
             } else {
-              e.x = (unsigned)off;
+              e.x = (unsigned)((long long)sy * pitch + (long long)sx * 3);
             }
             lut[base + kk * 256 + th] = e;
           }
-        items.push_back(make_int2(k, orient));
+        items.push_back(item);
         t.w++;
       }
       tiles.push_back(t);
@@ -563,12 +598,12 @@ int bevk_bev_finalize(bevk_ctx* c) {
   c->n_tiles = (long long)tiles.size();
   c->n_items = (long long)items.size();
   RET(c->d_tiles.ensure(tiles.size() * sizeof(int4)));
-  RET(c->d_items.ensure(std::max<size_t>(1, items.size()) * sizeof(int2)));
-  RET(c->d_lut.ensure(std::max<size_t>(1, lut.size()) * sizeof(uint2)));
+  RET(c->d_items.ensure(std::max<size_t>(1, items.size()) * sizeof(BevItem)));
+  RET(c->d_lut.ensure(std::max<size_t>(1, lut.size()) * sizeof(uint4)));
   CU(cudaMemcpyAsync(c->d_tiles.p, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
   if (!items.empty()) {
-    CU(cudaMemcpyAsync(c->d_items.p, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->d_lut.p, lut.data(), lut.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_items.p, items.data(), items.size() * sizeof(BevItem), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_lut.p, lut.data(), lut.size() * sizeof(uint4), cudaMemcpyHostToDevice, c->stream));
   }
   // OpenCV's 8-bit HSV division tables (color_hsv: sdiv_table / hdiv_table180, hsv_shift = 12)
   std::vector<int> tab(512, 0);
@@ -587,7 +622,9 @@ int bevk_bev_finalize(bevk_ctx* c) {
     const int nb[6] = {1, 4, 8, 1, 4, 8};
     for (int i = 0; i < 6; ++i) {
       int per_sm = 0;
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn[i], 256, bev_smem_bytes(nb[i])));
+      const size_t smem = bev_smem_bytes(i >= 3, nb[i]);
+      CU(cudaFuncSetAttribute(fn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn[i], 256, smem));
       c->bev_grid[i] = std::max(1, per_sm) * prop.multiProcessorCount;
     }
   }
@@ -600,7 +637,15 @@ int bevk_bev_plan_info(bevk_ctx* c, int64_t* n_tiles, int64_t* n_items, int64_t*
   if (!c->planned) return fail(BEVK_ERR_ARG, "bevk_bev_finalize not called");
   if (n_tiles) *n_tiles = c->n_tiles;
   if (n_items) *n_items = c->n_items;
-  if (lut_bytes) *lut_bytes = c->n_items * TILE * TILE * (int64_t)sizeof(uint2);
+  if (lut_bytes) *lut_bytes = c->n_items * TILE * TILE * (int64_t)sizeof(uint4);
+  return BEVK_OK;
+}
+
+int bevk_bev_stage_info(bevk_ctx* c, int64_t* staged_items, int64_t* staged_bytes) {
+  RET(use(c));
+  if (!c->planned) return fail(BEVK_ERR_ARG, "bevk_bev_finalize not called");
+  if (staged_items) *staged_items = c->staged_items;
+  if (staged_bytes) *staged_bytes = c->staged_bytes;
   return BEVK_OK;
 }
 
@@ -614,7 +659,7 @@ static int run_device(bevk_ctx* c, const void* d_srcs, int batch, const void* d_
   BevParams P{};
   P.srcs = reinterpret_cast<const uint8_t* const*>(d_srcs);
   P.n_cam = c->n_cam; P.FW = c->FW; P.FH = c->FH; P.pitch = (unsigned)c->FW * 3u;
-  P.tiles = c->d_tiles.as<int4>(); P.items = c->d_items.as<int2>(); P.lut = c->d_lut.as<uint2>();
+  P.tiles = c->d_tiles.as<int4>(); P.items = c->d_items.as<BevItem>(); P.lut = c->d_lut.as<uint4>();
   P.out = reinterpret_cast<uint8_t*>(d_out); P.BW = c->BW; P.BH = c->BH;
   P.canvas_bytes = (long long)c->BW * c->BH * 3;
   P.car = reinterpret_cast<const uint8_t*>(d_car);
@@ -622,6 +667,8 @@ static int run_device(bevk_ctx* c, const void* d_srcs, int batch, const void* d_
   P.cam_lo = cam_lo; P.cam_hi = cam_hi;
   P.tail_start = c->FW - (c->FW % 32);
   P.n_tiles = (int)c->n_tiles; P.batch = batch;
+  P.stage = 1;
+  if (const char* env = getenv("BEVK_STAGE")) P.stage = atoi(env) != 0;   // A/B switch for the TMA source staging
   // frame-sets per work unit: 4 amortises the LUT decode over a batch; 1 for single frames
   int nbu = batch >= 4 ? 4 : 1;
   if (const char* env = getenv("BEVK_NB")) {   // tuning override: 1, 4 or 8
@@ -631,7 +678,7 @@ static int run_device(bevk_ctx* c, const void* d_srcs, int batch, const void* d_
   const long long units = c->n_tiles * ((batch + nbu - 1) / nbu);
   const int variant = (bal ? 3 : 0) + (nbu == 8 ? 2 : (nbu == 4 ? 1 : 0));
   const unsigned bev_blocks = (unsigned)std::max<long long>(1, std::min<long long>(units, c->bev_grid[variant]));
-  const size_t bev_smem = bev_smem_bytes(nbu);
+  const size_t bev_smem = bev_smem_bytes(bal, nbu);
   if (c->timed) CU(cudaEventRecord(c->ev0, c->stream));
   if (bal) {
     const int nf = batch * c->n_cam;

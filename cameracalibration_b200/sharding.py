@@ -10,7 +10,7 @@ The reference is single-process (no collective anywhere); the path s
     NVLink, and each rank composes them with the saturating sum (bevk_sat_sum_device).  The
     compose is exact because cv2.add's saturation is order-independent on this path (blend
     weights sum to <= 255; plain seams overlap at most pairwise -- SURVEY 8a row a10), which
-    tests/test_sharding_gloo.py checks against the oracle.  balance=True is not available in
+    tests/test_sharding_gloo.py checks against the reference's result.  balance=True is not available in
     this mode (it needs the per-camera V sums before the warp).
 
 The pure partition functions below are what the world_size-2 gloo tests exercise on CPU.

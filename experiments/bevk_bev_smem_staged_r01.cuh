@@ -10,24 +10,25 @@
 // Work decomposition
 //   * canvas tiles of 32x32 px; per tile a list of "items" = cameras whose mask touches it;
 //   * per item a thread-ordered LUT block of 1024 x 16 B, fully decoded at plan time
-//     (bevk_bev_finalize):
-//       .x = byte offset of tap (sy,sx) in the frame            (border entries: sx | sy<<16)
-//       .y = w00 | w01 << 16, .z = w10 | w11 << 16              (bilinear weights as DP2A pairs)
-//       .w = blend multiplier (257*mask+1) | frac << 17 | flags << 28
-//     Lanes run along the canvas direction that walks source ROWS (orientation flag), so a
-//     warp's taps fall into 1-2 cache lines per row;
-//   * persistent CTAs (grid = resident CTAs) loop over (tile, group of NB frame-sets).  The LUT
-//     entry is fetched and decoded ONCE and applied to NB frame-sets, which amortises the
-//     table traffic and all the per-entry integer work over the batch;
-//   * taps: two aligned 32-bit loads per source row (+1 predicated when the 6 bytes straddle a
-//     third word), funnel-shifted into place; PRMT gathers the four taps of one channel into
-//     one register and two DP2A (16-bit weights x 8-bit pixels) produce  sum w*p + 512 ;
+//     (bevk_bev_finalize):  .x = byte offset of tap (sy,sx)  (in the staged source box, or in
+//     the frame for unstaged items; border entries: sx | sy<<16), .y/.z = the four bilinear
+//     weights as 16-bit pairs for DP2A, .w = blend multiplier | frac << 17 | flags << 28.
+//     Lanes run along the canvas direction that walks source ROWS (orientation flag);
+//   * persistent CTAs loop over (tile, group of NB frame-sets); a shared accumulator tile per
+//     frame-set takes the cameras in reference order (saturating add from the 2nd on);
+//   * SOURCE STAGING: for every (item, frame-set) the source bounding box of the tile (rows x
+//     row_bytes, computed at plan time) is brought into shared memory by the TMA engine --
+//     one cp.async.bulk per source row, issued by warp 0, completion on an mbarrier -- through
+//     a 3-deep ring that runs two boxes ahead of the math.  The gather then reads shared
+//     memory (two aligned 32-bit words per source row, +1 predicated), so the L1 tag/data
+//     path only sees the LUT.  Items whose box exceeds the ring slot (far-field tiles with
+//     strong minification), frames whose pitch is not a multiple of 16 B, and the BALANCE
+//     variant gather straight from global memory instead;
+//   * taps -> funnel shift -> PRMT gathers the four taps of one channel into one register ->
+//     two DP2A (16-bit weights x 8-bit pixels) give  sum w*p + 512 ;
 //   * the blend weight is an exact integer form of the reference's float expression:
 //       uint8(float32(px) * float32(mask/255.0)) == (px * (257*mask + 1)) >> 16   for all px, mask
-//     in 0..255 (mask 0 -> 0; mask 255 -> identity), checked exhaustively in tests/;
-//   * results go to a shared accumulator tile of packed BGRX words (saturating add for the
-//     2nd..nth camera, camera order = reference order) and leave with 32-bit stores, 12 B per
-//     thread.
+//     in 0..255 (mask 0 -> 0; mask 255 -> identity), checked exhaustively in tests/.
 #pragma once
 #include "bevk_device.cuh"
 
@@ -37,12 +38,18 @@ constexpr int TILE = 32;
 constexpr int ACC_WPITCH = TILE + 1;               // 33 words per row: rows and columns are both conflict-free
 constexpr int ACC_WORDS = TILE * ACC_WPITCH;       // 1056 words = 4224 B per frame-set
 constexpr unsigned LUT_ACTIVE = 1u << 28, LUT_BORDER = 2u << 28;
+constexpr int STAGE_SLOTS = 3;                     // ring depth: the producer runs two boxes ahead
+#ifndef BEVK_STAGE_CAP
+#define BEVK_STAGE_CAP 12288                       // bytes per ring slot (source box of one item, one frame)
+#endif
+constexpr int STAGE_CAP = BEVK_STAGE_CAP;
+constexpr int STAGE_SLOT_BYTES = STAGE_CAP + 128;  // slack: the word loads may run 8 B past the box
 
 struct BevItem {           // 32 B
   int cam, orient;         // orient 0: lanes along canvas x, 1: lanes along canvas y
-  int staged;              // reserved (shared-memory source staging, see experiments/)
-  unsigned src_off;
-  int rows, row_bytes;
+  int staged;              // 1: LUT offsets are relative to the staged source box
+  unsigned src_off;        // byte offset of the box origin in the frame (16-B aligned)
+  int rows, row_bytes;     // box: rows x row_bytes (row_bytes % 16 == 0)
   int pad0, pad1;
 };
 
@@ -61,8 +68,46 @@ struct BevParams {
   const int* hsv_tab;           // sdiv[256] ++ hdiv[256]
   int cam_lo, cam_hi;
   int tail_start;               // FW - FW % 32: first column of OpenCV's scalar HSV2BGR row tail
-  int stage;                    // reserved
+  int stage;                    // 0 disables source staging (tuning / A-B measurements)
 };
+
+// ---- mbarrier / bulk-copy (TMA) primitives -------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Ampere-style 16-byte async copy (SASS: LDGSTS) + "arrive on the mbarrier when my copies land"
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(unsigned long long* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+#ifndef BEVK_FILL
+#define BEVK_FILL 1   // 1: TMA bulk copy per source row, 2: cp.async 16-B chunks
+#endif
 
 __device__ __forceinline__ unsigned ldg32(const uint8_t* p) { return __ldg(reinterpret_cast<const unsigned*>(p)); }
 
@@ -78,14 +123,15 @@ __device__ __forceinline__ unsigned interp_fast(unsigned sh, unsigned wpx, unsig
   const unsigned ob = __dp2a_hi(wpy, pb, __dp2a_lo(wpx, pb, 512u)) >> 10;
   const unsigned og = __dp2a_hi(wpy, pg, __dp2a_lo(wpx, pg, 512u)) >> 10;
   const unsigned orr = __dp2a_hi(wpy, pr, __dp2a_lo(wpx, pr, 512u)) >> 10;
-  // BlendMask.__call__ / Mask.__call__ in exact integer form (see header)
-  // (v * wm) < 2^24 and the weighted value is its byte 2: pack the three byte-2s with two PRMTs
+  // BlendMask.__call__ / Mask.__call__ in exact integer form: (v * wm) < 2^24 and the weighted
+  // value is its byte 2 -- pack the three byte-2s with two PRMTs
   return __byte_perm(__byte_perm(ob * wm, og * wm, 0x0062), orr * wm, 0x7610);
 }
 
 // Slow path (kept out of line so the hot loop stays inside the instruction cache): entries with
 // out-of-frame taps (BORDER_CONSTANT 0 per tap; also every entry when the pitch is not a multiple
 // of 4) and the BALANCE variant, which runs OpenCV's 8-bit HSV round trip on each of the four taps.
+// `src` is the FRAME base; `off` is a frame offset (never a staged-box offset).
 struct SlowGeo { unsigned pitch; int FW, FH, tail_start; };
 template <bool BAL>
 __device__ __noinline__ unsigned sample_slow(const SlowGeo P, const uint8_t* __restrict__ src, unsigned ex, unsigned ew,
@@ -143,95 +189,172 @@ __device__ __forceinline__ unsigned sat_add_bgr(unsigned a, unsigned b) {
   return lo_s | (hi_s << 8);
 }
 
-// NB = frame-sets per work unit (1 for single-frame latency, 4/8 for batches).
-template <bool BAL, int NB>
+// The walk over this CTA's work: units (tile x frame-set group) -> items -> frame-sets of the
+// group.  Consumer (all warps) and producer (warp 0, running ahead) each keep one cursor and
+// advance it with the same rules, so they agree on which (item, frame-set) uses which ring slot.
+struct Cursor {
+  long long unit;     // current unit, or >= n_units when exhausted
+  int it, it_end;     // current item index / end of the unit's item list
+  int j;              // frame-set within the group
+  int b0, nb;
+};
+
+template <int NB>
+__device__ __forceinline__ void cursor_load_unit(const BevParams& P, Cursor& c, long long n_units) {
+  // position on the first accepted item of unit c.unit (or of a later unit); empty tiles are
+  // visited by the consumer separately (it must still write zeros), so stop on any unit here
+  if (c.unit < n_units) {
+    const int4 tile = P.tiles[(int)(c.unit % P.n_tiles)];
+    c.b0 = (int)(c.unit / P.n_tiles) * NB;
+    c.nb = min(NB, P.batch - c.b0);
+    c.it = tile.z; c.it_end = tile.z + tile.w; c.j = 0;
+  }
+}
+
+// NB = frame-sets per work unit (1 for single-frame latency, 4 for batches).
 #ifndef BEVK_MIN_CTAS
 #define BEVK_MIN_CTAS 4
 #endif
+template <bool BAL, int NB>
 __global__ void __launch_bounds__(256, BEVK_MIN_CTAS) k_bev(BevParams P) {
-  extern __shared__ __align__(16) unsigned smem_w[];
-  unsigned* acc = smem_w;                                   // [NB][ACC_WORDS] packed BGRX
-  int* s_hsv = reinterpret_cast<int*>(smem_w + NB * ACC_WORDS);   // [512] (BALANCE)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* ring = smem_raw;                                                  // [STAGE_SLOTS][STAGE_SLOT_BYTES] (not BAL)
+  unsigned* acc = reinterpret_cast<unsigned*>(smem_raw + (BAL ? 0 : STAGE_SLOTS * STAGE_SLOT_BYTES));   // [NB][ACC_WORDS] BGRX
+  int* s_hsv = reinterpret_cast<int*>(acc + NB * ACC_WORDS);                       // [512] (BALANCE)
   __shared__ unsigned long long s_sum[BAL ? 3 * NB : 1];
+  __shared__ __align__(8) unsigned long long bar_full[STAGE_SLOTS], bar_empty[STAGE_SLOTS];
   const int t = threadIdx.x, lane = t & 31, wrp = t >> 5;
+  const bool staging = !BAL && P.stage;
   if (BAL) {
     s_hsv[t] = P.hsv_tab[t]; s_hsv[t + 256] = P.hsv_tab[t + 256];
     if (t < 3 * NB) s_sum[t] = 0ull;
+  }
+  if (t == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGE_SLOTS; ++s) { mbar_init(&bar_full[s], BEVK_FILL == 1 ? 1 : 32); mbar_init(&bar_empty[s], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const int groups = (P.batch + NB - 1) / NB;
   const long long n_units = (long long)P.n_tiles * groups;
   // accumulator word of this thread's first pixel / step to the next one, per orientation
   const int posx = (wrp * 4) * ACC_WPITCH + lane, stepx = ACC_WPITCH;   // lanes along x, k walks rows
   const int posy = lane * ACC_WPITCH + wrp * 4, stepy = 1;              // lanes along y, k walks columns
+  __syncthreads();
+
+  // ---- producer state (warp 0): cursor two fills ahead, ring position -----------------
+  Cursor pc;
+  pc.unit = blockIdx.x;
+  cursor_load_unit<NB>(P, pc, n_units);
+  unsigned p_fill = 0;      // fills issued so far (slot = p_fill % STAGE_SLOTS)
+  unsigned c_fill = 0;      // fills consumed so far
+
+  // issue boxes until the ring is full or the work is exhausted (warp 0 only, warp-uniform)
+  auto produce = [&]() {
+    while (pc.unit < n_units && p_fill - c_fill < (unsigned)STAGE_SLOTS) {
+      if (pc.it >= pc.it_end) {           // next unit
+        pc.unit += gridDim.x;
+        cursor_load_unit<NB>(P, pc, n_units);
+        continue;
+      }
+      const BevItem item = P.items[pc.it];
+      const bool take = item.cam >= P.cam_lo && item.cam < P.cam_hi && item.staged;
+      if (take) {
+        const int b = pc.b0 + pc.j;
+        const uint8_t* src = P.srcs[b * P.n_cam + item.cam];
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {      // same test on the consumer side
+          const unsigned slot = p_fill % STAGE_SLOTS;
+          if (p_fill >= (unsigned)STAGE_SLOTS) mbar_wait(&bar_empty[slot], ((p_fill / STAGE_SLOTS) - 1) & 1);
+          unsigned char* dst = ring + slot * STAGE_SLOT_BYTES;
+          const uint8_t* s0 = src + item.src_off;
+#if BEVK_FILL == 1
+          if (lane == 0) mbar_expect_tx(&bar_full[slot], (unsigned)(item.rows * item.row_bytes));
+          __syncwarp();
+          for (int r = lane; r < item.rows; r += 32)
+            tma_bulk_g2s(dst + r * item.row_bytes, s0 + (size_t)r * P.pitch, (unsigned)item.row_bytes, &bar_full[slot]);
+#else
+          const int cpr = item.row_bytes >> 4, n16 = item.rows * cpr;   // 16-byte chunks per row / in the box
+          for (int q = lane; q < n16; q += 32) {
+            const int r = q / cpr, cix = q - r * cpr;
+            cp_async16(dst + r * item.row_bytes + cix * 16, s0 + (size_t)r * P.pitch + cix * 16);
+          }
+          cp_async_arrive(&bar_full[slot]);
+#endif
+          ++p_fill;
+        }
+      }
+      if (++pc.j >= pc.nb) { pc.j = 0; ++pc.it; }
+    }
+  };
 
   for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
     const int tile_id = (int)(unit % P.n_tiles);
     const int b0 = (int)(unit / P.n_tiles) * NB;
     const int nb = min(NB, P.batch - b0);
     const int4 tile = P.tiles[tile_id];
-    __syncthreads();   // previous unit's write-out (and the table fill on the first pass) is done
+    __syncthreads();   // previous unit's write-out is done with the accumulator
     bool first = true;   // no camera has written this tile yet: the first one stores (zeros where masked out)
     for (int it = tile.z; it < tile.z + tile.w; ++it) {
       const BevItem item = P.items[it];
       if (item.cam < P.cam_lo || item.cam >= P.cam_hi) continue;
       const uint4* __restrict__ L = P.lut + (size_t)it * (TILE * TILE) + t;
-      const uint8_t* src[NB];
-      int dl[NB];
-#pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        const int b = b0 + (j < nb ? j : 0);   // j >= nb aliases frame-set b0: computed, never written out
-        src[j] = P.srcs[b * P.n_cam + item.cam];
-        dl[j] = BAL ? P.delta[b * P.n_cam + item.cam] : 0;
-      }
       const int pos = item.orient ? posy : posx, step = item.orient ? stepy : stepx;
-      uint4 nxt = __ldg(L);
+      const SlowGeo geo = {P.pitch, P.FW, P.FH, P.tail_start};
 #pragma unroll 1
-      for (int k = 0; k < 4; ++k) {
-        const uint4 e = nxt;
-        if (k < 3) nxt = __ldg(L + (k + 1) * 256);   // prefetch the next entry under this one's work
-        unsigned* a = acc + pos + k * step;
-        if (!(e.w & LUT_ACTIVE)) {
-          if (first) {
-#pragma unroll
-            for (int j = 0; j < NB; ++j) a[j * ACC_WORDS] = 0u;
-          }
-          continue;
+      for (int j = 0; j < nb; ++j) {
+        const int b = b0 + j;
+        const uint8_t* src = P.srcs[b * P.n_cam + item.cam];
+        const int dl = BAL ? P.delta[b * P.n_cam + item.cam] : 0;
+        const bool staged = staging && item.staged && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+        const unsigned char* box = nullptr;
+        unsigned slot = 0;
+        if (staging && wrp == 0) produce();
+        if (staged) {
+          slot = c_fill % STAGE_SLOTS;
+          mbar_wait(&bar_full[slot], (c_fill / STAGE_SLOTS) & 1);
+          box = ring + slot * STAGE_SLOT_BYTES;
         }
-        if (BAL || (e.w & LUT_BORDER)) {
-          const SlowGeo geo = {P.pitch, P.FW, P.FH, P.tail_start};
-#pragma unroll
-          for (int j = 0; j < NB; ++j) {
-            unsigned v = sample_slow<BAL>(geo, src[j], e.x, e.w, dl[j], s_hsv);
-            if (!first) v = sat_add_bgr(v, a[j * ACC_WORDS]);
-            a[j * ACC_WORDS] = v;
+        unsigned* accj = acc + j * ACC_WORDS + pos;
+        uint4 nxt = __ldg(L);
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+          const uint4 e = nxt;
+          if (k < 3) nxt = __ldg(L + (k + 1) * 256);   // prefetch the next entry under this one's work
+          unsigned* a = accj + k * step;
+          if (!(e.w & LUT_ACTIVE)) {
+            if (first) *a = 0u;
+            continue;
           }
-        } else {
-          // phase 1: every tap load of the NB frame-sets in flight before any is consumed;
-          // phase 2: interpolate, weight, accumulate (cv2.add order: front, back, left, right)
-          const unsigned off_al = e.x & ~3u, sh = (e.x & 3u) * 8u, wm = e.w & 0x1ffffu;
-          const bool third = (sh == 24u);
-          unsigned a0[NB], a1[NB], a2[NB], b0w[NB], b1w[NB], b2w[NB];
-#pragma unroll
-          for (int j = 0; j < NB; ++j) {
-            const uint8_t* q0 = src[j] + off_al;
-            const uint8_t* q1 = q0 + P.pitch;
-            a0[j] = ldg32(q0); a1[j] = ldg32(q0 + 4); a2[j] = third ? ldg32(q0 + 8) : 0u;
-            b0w[j] = ldg32(q1); b1w[j] = ldg32(q1 + 4); b2w[j] = third ? ldg32(q1 + 8) : 0u;
-          }
-          if (first) {
-#pragma unroll
-            for (int j = 0; j < NB; ++j)
-              a[j * ACC_WORDS] = interp_fast(sh, e.y, e.z, wm, a0[j], a1[j], a2[j], b0w[j], b1w[j], b2w[j]);
+          unsigned v;
+          if (BAL || (e.w & LUT_BORDER)) {
+            v = sample_slow<BAL>(geo, src, e.x, e.w, dl, s_hsv);
           } else {
-#pragma unroll
-            for (int j = 0; j < NB; ++j)
-              a[j * ACC_WORDS] =
-                  sat_add_bgr(interp_fast(sh, e.y, e.z, wm, a0[j], a1[j], a2[j], b0w[j], b1w[j], b2w[j]), a[j * ACC_WORDS]);
+            const unsigned off_al = e.x & ~3u, sh = (e.x & 3u) * 8u;
+            const bool third = (sh == 24u);
+            unsigned a0, a1, a2 = 0u, b0w, b1w, b2w = 0u;
+            if (staged) {
+              const unsigned* q0 = reinterpret_cast<const unsigned*>(box + off_al);
+              const unsigned* q1 = reinterpret_cast<const unsigned*>(box + off_al + item.row_bytes);
+              a0 = q0[0]; a1 = q0[1]; b0w = q1[0]; b1w = q1[1];
+              if (third) { a2 = q0[2]; b2w = q1[2]; }
+            } else {
+              const uint8_t* q0 = src + off_al;
+              const uint8_t* q1 = q0 + P.pitch;
+              a0 = ldg32(q0); a1 = ldg32(q0 + 4); b0w = ldg32(q1); b1w = ldg32(q1 + 4);
+              if (third) { a2 = ldg32(q0 + 8); b2w = ldg32(q1 + 8); }
+            }
+            v = interp_fast(sh, e.y, e.z, e.w & 0x1ffffu, a0, a1, a2, b0w, b1w, b2w);
           }
+          if (!first) v = sat_add_bgr(v, *a);   // cv2.add, camera order front, back, left, right
+          *a = v;
+        }
+        if (staged) {      // this warp is done with the slot: let the producer refill it
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_empty[slot]);
+          ++c_fill;
         }
       }
       first = false;
-      __syncthreads();
+      __syncthreads();   // the next camera of this tile may touch the same pixels from other threads
     }
     // ---- write the tile(s): thread t -> row t/8, 4 pixels (12 bytes) at pixel 4*(t%8) ----
     const int row = t >> 3, chunk = t & 7;
@@ -295,6 +418,8 @@ __global__ void __launch_bounds__(256, BEVK_MIN_CTAS) k_bev(BevParams P) {
   }
 }
 
-constexpr size_t bev_smem_bytes(bool /*bal*/, int nb) { return (size_t)nb * ACC_WORDS * 4 + 512 * sizeof(int); }
+constexpr size_t bev_smem_bytes(bool bal, int nb) {
+  return (bal ? 0 : (size_t)STAGE_SLOTS * STAGE_SLOT_BYTES) + (size_t)nb * ACC_WORDS * 4 + 512 * sizeof(int);
+}
 
 }  // namespace bevk

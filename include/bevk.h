@@ -146,6 +146,9 @@ int bevk_luminance_balance(bevk_ctx *ctx, const uint8_t *const *imgs, int n, int
 
 /* Introspection for tests / bench */
 int bevk_bev_plan_info(bevk_ctx *ctx, int64_t *n_tiles, int64_t *n_items, int64_t *lut_bytes);
+/* Items whose source box is staged in shared memory by TMA, and the bytes those boxes
+ * move per frame-set (the rest of the items gather straight from global memory). */
+int bevk_bev_stage_info(bevk_ctx *ctx, int64_t *staged_items, int64_t *staged_bytes_per_frame_set);
 /* Kernel launches issued by this ctx since creation (bench "gpu_launches"). */
 int64_t bevk_launch_count(bevk_ctx *ctx);
 /* Milliseconds spent in the last bevk_bev_run_device call's kernels, measured with
