@@ -120,6 +120,9 @@ struct bevk_ctx {
   int device = 0;
   cudaStream_t own = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t copy_stream = nullptr;                      // H2D side of the host-pointer pipeline
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  const void* ptrs_for = nullptr; const void* ptrs_tab = nullptr; long long ptrs_n = 0; size_t ptrs_pad = 0;   // cached frame pointer table
   bool timed = false;
   long long launches = 0;
   DevBuf s_src, s_dst, s_m1, s_m2, s_o1, s_o2;   // scratch for the host-pointer entry points
@@ -180,6 +183,11 @@ int bevk_ctx_destroy(bevk_ctx* c) {
   for (auto& k : c->cam) { k.map1.release(); k.map2.release(); }
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_free[i]); }
+    cudaStreamDestroy(c->copy_stream);
+  }
   cudaStreamDestroy(c->own);
   delete c;
   return BEVK_OK;
@@ -753,34 +761,56 @@ int bevk_bev_run(bevk_ctx* c, const uint8_t* const* srcs, int64_t src_stride, in
   const size_t row = (size_t)c->FW * 3, fbytes = row * c->FH, fpad = (fbytes + 255) & ~size_t(255);
   if (src_stride < (int64_t)row) return fail(BEVK_ERR_ARG, "src_stride %lld < row bytes", (long long)src_stride);
   const size_t cbytes = (size_t)c->BW * c->BH * 3;
-  const int chunk_max = 64;   // frame-sets resident at once (64 x 4 x 1080p = 1.6 GB)
-  const int chunk = std::min(batch, chunk_max);
-  RET(c->d_frames.ensure(fpad * c->n_cam * chunk));
-  RET(c->d_ptrs.ensure(sizeof(void*) * c->n_cam * chunk));
-  RET(c->d_canvas.ensure(cbytes * chunk));
+  // Two-deep pipeline over chunks of frame-sets: the H2D copies of chunk i+1 run on the copy
+  // stream while chunk i is rendered and its canvases go back on the main stream, so the two
+  // PCIe directions overlap and the kernel hides under the copies.
+  const int chunk = std::min(batch, 8);
+  const size_t set_frames = (size_t)c->n_cam;
+  RET(c->d_frames.ensure(fpad * set_frames * chunk * 2));
+  RET(c->d_ptrs.ensure(sizeof(void*) * set_frames * chunk * 2));
+  RET(c->d_canvas.ensure(cbytes * chunk * 2));
+  if (!c->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CU(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+    }
+  }
   if (car) {
     RET(c->d_car.ensure(cbytes));
     CU(cudaMemcpyAsync(c->d_car.p, car, cbytes, cudaMemcpyHostToDevice, c->stream));
   }
-  {
-    std::vector<const uint8_t*> ptrs((size_t)c->n_cam * chunk);
+  if (c->ptrs_for != c->d_frames.p || c->ptrs_tab != c->d_ptrs.p || c->ptrs_n != (long long)(set_frames * chunk * 2) || c->ptrs_pad != fpad) {
+    std::vector<const uint8_t*> ptrs(set_frames * chunk * 2);
     for (size_t i = 0; i < ptrs.size(); ++i) ptrs[i] = c->d_frames.as<uint8_t>() + i * fpad;
     CU(cudaMemcpyAsync(c->d_ptrs.p, ptrs.data(), ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));   // ptrs is a stack-lifetime staging vector
+    c->ptrs_for = c->d_frames.p; c->ptrs_tab = c->d_ptrs.p; c->ptrs_n = (long long)ptrs.size(); c->ptrs_pad = fpad;
   }
-  for (int b0 = 0; b0 < batch; b0 += chunk) {
+  // the copy stream must not start before work already queued on the main stream (e.g. the car upload,
+  // or a previous call's D2H that still reads the canvases) has been ordered
+  CU(cudaEventRecord(c->ev_free[0], c->stream));
+  CU(cudaEventRecord(c->ev_free[1], c->stream));
+  int half = 0;
+  for (int b0 = 0; b0 < batch; b0 += chunk, half ^= 1) {
     const int nb = std::min(chunk, batch - b0);
+    uint8_t* dframes = c->d_frames.as<uint8_t>() + (size_t)half * chunk * set_frames * fpad;
+    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_free[half], 0));   // this half's previous chunk has been rendered
     for (int i = 0; i < nb * c->n_cam; ++i) {
       const uint8_t* s = srcs[(size_t)b0 * c->n_cam + i];
       if (!s) return fail(BEVK_ERR_ARG, "null frame pointer %d", b0 * c->n_cam + i);
-      uint8_t* d = c->d_frames.as<uint8_t>() + (size_t)i * fpad;
-      if ((size_t)src_stride == row) CU(cudaMemcpyAsync(d, s, fbytes, cudaMemcpyHostToDevice, c->stream));
-      else CU(cudaMemcpy2DAsync(d, row, s, (size_t)src_stride, row, c->FH, cudaMemcpyHostToDevice, c->stream));
+      uint8_t* d = dframes + (size_t)i * fpad;
+      if ((size_t)src_stride == row) CU(cudaMemcpyAsync(d, s, fbytes, cudaMemcpyHostToDevice, c->copy_stream));
+      else CU(cudaMemcpy2DAsync(d, row, s, (size_t)src_stride, row, c->FH, cudaMemcpyHostToDevice, c->copy_stream));
     }
+    CU(cudaEventRecord(c->ev_in[half], c->copy_stream));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_in[half], 0));
     c->timed = false;
-    RET(run_device(c, c->d_ptrs.p, nb, car ? c->d_car.p : nullptr, flags, c->d_canvas.p, 0, BEVK_MAX_CAMERAS));
-    CU(cudaMemcpyAsync(out + (size_t)b0 * cbytes, c->d_canvas.p, cbytes * nb, cudaMemcpyDeviceToHost, c->stream));
-    if (b0 + chunk < batch) CU(cudaStreamSynchronize(c->stream));   // the frame buffers are reused by the next chunk
+    uint8_t* dcanvas = c->d_canvas.as<uint8_t>() + (size_t)half * chunk * cbytes;
+    const void* dptrs = c->d_ptrs.as<const uint8_t*>() + (size_t)half * chunk * set_frames;
+    RET(run_device(c, dptrs, nb, car ? c->d_car.p : nullptr, flags, dcanvas, 0, BEVK_MAX_CAMERAS));
+    CU(cudaEventRecord(c->ev_free[half], c->stream));               // frames of this half are free again
+    CU(cudaMemcpyAsync(out + (size_t)b0 * cbytes, dcanvas, cbytes * nb, cudaMemcpyDeviceToHost, c->stream));
   }
   CU(cudaStreamSynchronize(c->stream));
   return BEVK_OK;
@@ -848,6 +878,7 @@ int bevk_luminance_balance(bevk_ctx* c, const uint8_t* const* imgs, int n, int w
   RET(c->s_src.ensure(fpad * n));
   RET(c->s_dst.ensure(fpad * n));
   RET(c->d_ptrs.ensure(sizeof(void*) * 2 * BEVK_MAX_CAMERAS));
+  c->ptrs_for = nullptr;   // the BEV host path's cached pointer table is overwritten below
   RET(c->d_vsum.ensure(8 * n));
   RET(c->d_delta.ensure(4 * n));
   const uint8_t* ptrs[2 * BEVK_MAX_CAMERAS];

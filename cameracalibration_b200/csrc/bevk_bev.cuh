@@ -83,6 +83,30 @@ __device__ __forceinline__ unsigned interp_fast(unsigned sh, unsigned wpx, unsig
   return __byte_perm(__byte_perm(ob * wm, og * wm, 0x0062), orr * wm, 0x7610);
 }
 
+// BALANCE variant of interp_fast: OpenCV's 8-bit BGR -> HSV -> (V + delta) -> BGR round trip
+// (luminance_balance, surroundBEV.py:57-79) on each of the four taps, then the same Q10
+// interpolation and weight.  tail0/tail1: the left/right tap columns lie in OpenCV's rounding row tail.
+__device__ __forceinline__ unsigned interp_bal(unsigned sh, unsigned ew, unsigned a0, unsigned a1, unsigned a2, unsigned b0,
+                                               unsigned b1, unsigned b2, int delta, bool tail0, bool tail1,
+                                               const int* s_hsv) {
+  const unsigned A = __funnelshift_r(a0, a1, sh), A2 = __funnelshift_r(a1, a2, sh);
+  const unsigned B = __funnelshift_r(b0, b1, sh), B2 = __funnelshift_r(b1, b2, sh);
+  int p00b = A & 255u, p00g = (A >> 8) & 255u, p00r = (A >> 16) & 255u;
+  int p01b = A >> 24, p01g = A2 & 255u, p01r = (A2 >> 8) & 255u;
+  int p10b = B & 255u, p10g = (B >> 8) & 255u, p10r = (B >> 16) & 255u;
+  int p11b = B >> 24, p11g = B2 & 255u, p11r = (B2 >> 8) & 255u;
+  hsv_roundtrip(p00b, p00g, p00r, delta, tail0, s_hsv, s_hsv + 256);
+  hsv_roundtrip(p01b, p01g, p01r, delta, tail1, s_hsv, s_hsv + 256);
+  hsv_roundtrip(p10b, p10g, p10r, delta, tail0, s_hsv, s_hsv + 256);
+  hsv_roundtrip(p11b, p11g, p11r, delta, tail1, s_hsv, s_hsv + 256);
+  const int fx = (ew >> 17) & 31, fy = (ew >> 22) & 31;
+  const unsigned wm = ew & 0x1ffffu;
+  const unsigned ob = (unsigned)bilerp_q10(p00b, p01b, p10b, p11b, fx, fy);
+  const unsigned og = (unsigned)bilerp_q10(p00g, p01g, p10g, p11g, fx, fy);
+  const unsigned orr = (unsigned)bilerp_q10(p00r, p01r, p10r, p11r, fx, fy);
+  return __byte_perm(__byte_perm(ob * wm, og * wm, 0x0062), orr * wm, 0x7610);
+}
+
 // Slow path (kept out of line so the hot loop stays inside the instruction cache): entries with
 // out-of-frame taps (BORDER_CONSTANT 0 per tap; also every entry when the pitch is not a multiple
 // of 4) and the BALANCE variant, which runs OpenCV's 8-bit HSV round trip on each of the four taps.
@@ -197,7 +221,7 @@ __global__ void __launch_bounds__(256, BEVK_MIN_CTAS) k_bev(BevParams P) {
           }
           continue;
         }
-        if (BAL || (e.w & LUT_BORDER)) {
+        if (e.w & LUT_BORDER) {
           const SlowGeo geo = {P.pitch, P.FW, P.FH, P.tail_start};
 #pragma unroll
           for (int j = 0; j < NB; ++j) {
@@ -218,7 +242,19 @@ __global__ void __launch_bounds__(256, BEVK_MIN_CTAS) k_bev(BevParams P) {
             a0[j] = ldg32(q0); a1[j] = ldg32(q0 + 4); a2[j] = third ? ldg32(q0 + 8) : 0u;
             b0w[j] = ldg32(q1); b1w[j] = ldg32(q1 + 4); b2w[j] = third ? ldg32(q1 + 8) : 0u;
           }
-          if (first) {
+          if (BAL) {
+            bool tail0 = false, tail1 = false;
+            if (P.tail_start != P.FW) {   // only frames whose width is not a multiple of 32 have a rounding tail
+              const int sx0 = (int)((e.x % P.pitch) / 3u);
+              tail0 = sx0 >= P.tail_start; tail1 = sx0 + 1 >= P.tail_start;
+            }
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+              unsigned v = interp_bal(sh, e.w, a0[j], a1[j], a2[j], b0w[j], b1w[j], b2w[j], dl[j], tail0, tail1, s_hsv);
+              if (!first) v = sat_add_bgr(v, a[j * ACC_WORDS]);
+              a[j * ACC_WORDS] = v;
+            }
+          } else if (first) {
 #pragma unroll
             for (int j = 0; j < NB; ++j)
               a[j * ACC_WORDS] = interp_fast(sh, e.y, e.z, wm, a0[j], a1[j], a2[j], b0w[j], b1w[j], b2w[j]);
