@@ -1,0 +1,454 @@
+// bevk_bev.cuh -- the fused per-frame surround-BEV kernel (sm_100a).
+//
+// Reference path fused here (SurroundBirdEyeView/surroundBEV.py:312-325): for every
+// camera  raw2bev = cv2.remap(img, bev_map1, bev_map2, INTER_LINEAR)  (:116-117), then
+// Mask / BlendMask.__call__ (:161-162 / :279-280), then the saturating cv2.add chain
+// (:318-320), the optional car overlay (:323-324), and -- in the BALANCE variant --
+// luminance_balance applied lazily to the sampled taps (:57-79) plus the channel sums
+// color_balance needs (:44-47).  No intermediate image is written to HBM.
+//
+// Work decomposition
+//   * canvas tiles of 32x32 px; per tile a list of "items" = cameras whose mask touches it;
+//   * per item a thread-ordered LUT block of 1024 x 16 B, fully decoded at plan time
+//     (bevk_bev_finalize):
+//       .x = byte offset of tap (sy,sx) in the frame            (border entries: sx | sy<<16)
+//       .y = w00 | w01 << 16, .z = w10 | w11 << 16              (bilinear weights as DP2A pairs)
+//       .w = blend multiplier (257*mask+1) | frac << 17 | flags << 28
+//     Lanes run along the canvas direction that walks source ROWS (orientation flag), so a
+//     warp's taps fall into 1-2 cache lines per row;
+//   * persistent CTAs (grid = resident CTAs) loop over (tile, group of NB frame-sets).  The LUT
+//     entry is fetched and decoded ONCE and applied to NB frame-sets, which amortises the
+//     table traffic and all the per-entry integer work over the batch;
+//   * taps: two aligned 32-bit loads per source row (+1 predicated when the 6 bytes straddle a
+//     third word), funnel-shifted into place; PRMT gathers the four taps of one channel into
+//     one register and two DP2A (16-bit weights x 8-bit pixels) produce  sum w*p + 512 ;
+//   * the blend weight is an exact integer form of the reference's float expression:
+//       uint8(float32(px) * float32(mask/255.0)) == (px * (257*mask + 1)) >> 16   for all px, mask
+//     in 0..255 (mask 0 -> 0; mask 255 -> identity), checked exhaustively in tests/;
+//   * results go to a shared accumulator tile of packed BGRX words (saturating add for the
+//     2nd..nth camera, camera order = reference order) and leave with 32-bit stores, 12 B per
+//     thread.
+#pragma once
+#include "bevk_device.cuh"
+
+namespace bevk {
+
+constexpr int TILE = 32;
+constexpr int ACC_WPITCH = TILE + 1;               // 33 words per row: rows and columns are both conflict-free
+constexpr int ACC_WORDS = TILE * ACC_WPITCH;       // 1056 words = 4224 B per frame-set
+constexpr unsigned LUT_ACTIVE = 1u << 28, LUT_BORDER = 2u << 28;
+
+struct BevItem {           // 32 B
+  int cam, orient;         // orient 0: lanes along canvas x, 1: lanes along canvas y
+  int staged;              // reserved (shared-memory source staging, see experiments/)
+  unsigned src_off;
+  int rows, row_bytes;
+  int pad0, pad1;
+};
+
+struct BevParams {
+  const uint8_t* const* srcs;   // device array [batch * n_cam] of dense BGR frames
+  int n_cam, FW, FH;
+  unsigned pitch;               // source row pitch in bytes (= 3*FW)
+  const int4* tiles;            // x0, y0, first item, item count
+  const BevItem* items;
+  const uint4* lut;             // [item][4][256]
+  int n_tiles, batch;
+  uint8_t* out; int BW, BH; long long canvas_bytes;
+  const uint8_t* car;
+  const int* delta;             // [batch * n_cam] luminance offsets (BALANCE)
+  unsigned long long* csum;     // [batch * 3] channel sums of the composed canvas (BALANCE)
+  const int* hsv_tab;           // sdiv[256] ++ hdiv[256]
+  int cam_lo, cam_hi;
+  int tail_start;               // FW - FW % 32: first column of OpenCV's scalar HSV2BGR row tail
+  int stage;                    // reserved
+};
+
+__device__ __forceinline__ unsigned ldg32(const uint8_t* p) { return __ldg(reinterpret_cast<const unsigned*>(p)); }
+
+// Fast path, phase 2: the six words of one entry -> weighted pixel packed B | G<<8 | R<<16.
+__device__ __forceinline__ unsigned interp_fast(unsigned sh, unsigned wpx, unsigned wpy, unsigned wm, unsigned a0, unsigned a1,
+                                                unsigned a2, unsigned b0, unsigned b1, unsigned b2) {
+  const unsigned A = __funnelshift_r(a0, a1, sh), A2 = __funnelshift_r(a1, a2, sh);   // B0 G0 R0 B1 | G1 R1 . .
+  const unsigned B = __funnelshift_r(b0, b1, sh), B2 = __funnelshift_r(b1, b2, sh);
+  // four taps of one channel per register: [p00 p01 p10 p11]
+  const unsigned pb = __byte_perm(A, B, 0x7430);
+  const unsigned pg = __byte_perm(__byte_perm(A, A2, 0x0041), __byte_perm(B, B2, 0x0041), 0x5410);
+  const unsigned pr = __byte_perm(__byte_perm(A, A2, 0x0052), __byte_perm(B, B2, 0x0052), 0x5410);
+  const unsigned ob = __dp2a_hi(wpy, pb, __dp2a_lo(wpx, pb, 512u)) >> 10;
+  const unsigned og = __dp2a_hi(wpy, pg, __dp2a_lo(wpx, pg, 512u)) >> 10;
+  const unsigned orr = __dp2a_hi(wpy, pr, __dp2a_lo(wpx, pr, 512u)) >> 10;
+  // BlendMask.__call__ / Mask.__call__ in exact integer form (see header)
+  // (v * wm) < 2^24 and the weighted value is its byte 2: pack the three byte-2s with two PRMTs
+  return __byte_perm(__byte_perm(ob * wm, og * wm, 0x0062), orr * wm, 0x7610);
+}
+
+// BALANCE variant of interp_fast: OpenCV's 8-bit BGR -> HSV -> (V + delta) -> BGR round trip
+// (luminance_balance, surroundBEV.py:57-79) on each of the four taps, then the same Q10
+// interpolation and weight.  tail0/tail1: the left/right tap columns lie in OpenCV's rounding row tail.
+__device__ __forceinline__ unsigned interp_bal(unsigned sh, unsigned ew, unsigned a0, unsigned a1, unsigned a2, unsigned b0,
+                                               unsigned b1, unsigned b2, int delta, bool tail0, bool tail1,
+                                               const int* s_hsv) {
+  const unsigned A = __funnelshift_r(a0, a1, sh), A2 = __funnelshift_r(a1, a2, sh);
+  const unsigned B = __funnelshift_r(b0, b1, sh), B2 = __funnelshift_r(b1, b2, sh);
+  int p00b = A & 255u, p00g = (A >> 8) & 255u, p00r = (A >> 16) & 255u;
+  int p01b = A >> 24, p01g = A2 & 255u, p01r = (A2 >> 8) & 255u;
+  int p10b = B & 255u, p10g = (B >> 8) & 255u, p10r = (B >> 16) & 255u;
+  int p11b = B >> 24, p11g = B2 & 255u, p11r = (B2 >> 8) & 255u;
+  hsv_roundtrip(p00b, p00g, p00r, delta, tail0, s_hsv, s_hsv + 256);
+  hsv_roundtrip(p01b, p01g, p01r, delta, tail1, s_hsv, s_hsv + 256);
+  hsv_roundtrip(p10b, p10g, p10r, delta, tail0, s_hsv, s_hsv + 256);
+  hsv_roundtrip(p11b, p11g, p11r, delta, tail1, s_hsv, s_hsv + 256);
+  const int fx = (ew >> 17) & 31, fy = (ew >> 22) & 31;
+  const unsigned wm = ew & 0x1ffffu;
+  const unsigned ob = (unsigned)bilerp_q10(p00b, p01b, p10b, p11b, fx, fy);
+  const unsigned og = (unsigned)bilerp_q10(p00g, p01g, p10g, p11g, fx, fy);
+  const unsigned orr = (unsigned)bilerp_q10(p00r, p01r, p10r, p11r, fx, fy);
+  return __byte_perm(__byte_perm(ob * wm, og * wm, 0x0062), orr * wm, 0x7610);
+}
+
+// Slow path (kept out of line so the hot loop stays inside the instruction cache): entries with
+// out-of-frame taps (BORDER_CONSTANT 0 per tap; also every entry when the pitch is not a multiple
+// of 4) and the BALANCE variant, which runs OpenCV's 8-bit HSV round trip on each of the four taps.
+struct SlowGeo { unsigned pitch; int FW, FH, tail_start; };
+template <bool BAL>
+__device__ __noinline__ unsigned sample_slow(const SlowGeo P, const uint8_t* __restrict__ src, unsigned ex, unsigned ew,
+                                             int delta, const int* s_hsv) {
+  int p[4][3];
+  const unsigned wm = ew & 0x1ffffu;
+  if (ew & LUT_BORDER) {
+    const int sx = (short)(ex & 0xffffu), sy = (short)(ex >> 16);
+#pragma unroll 1
+    for (int t = 0; t < 4; ++t) {
+      const int tx = sx + (t & 1), ty = sy + (t >> 1);
+      const bool in = ((unsigned)tx < (unsigned)P.FW) && ((unsigned)ty < (unsigned)P.FH);
+      int c0 = 0, c1 = 0, c2 = 0;
+      if (in) {
+        const uint8_t* q = src + (size_t)ty * P.pitch + 3 * tx;
+        c0 = __ldg(q); c1 = __ldg(q + 1); c2 = __ldg(q + 2);
+        if (BAL) hsv_roundtrip(c0, c1, c2, delta, tx >= P.tail_start, s_hsv, s_hsv + 256);
+      }   // else: the border constant is not an image pixel, no balance
+      p[t][0] = c0; p[t][1] = c1; p[t][2] = c2;
+    }
+  } else {
+    const unsigned off_al = ex & ~3u, sh = (ex & 3u) * 8u;
+    const uint8_t* q0 = src + off_al;
+    const uint8_t* q1 = q0 + P.pitch;
+    const bool third = (sh == 24u);
+    const unsigned a0 = ldg32(q0), a1 = ldg32(q0 + 4), a2 = third ? ldg32(q0 + 8) : 0u;
+    const unsigned b0 = ldg32(q1), b1 = ldg32(q1 + 4), b2 = third ? ldg32(q1 + 8) : 0u;
+    const unsigned A = __funnelshift_r(a0, a1, sh), A2 = __funnelshift_r(a1, a2, sh);
+    const unsigned B = __funnelshift_r(b0, b1, sh), B2 = __funnelshift_r(b1, b2, sh);
+    p[0][0] = A & 255u; p[0][1] = (A >> 8) & 255u; p[0][2] = (A >> 16) & 255u;
+    p[1][0] = A >> 24;  p[1][1] = A2 & 255u;       p[1][2] = (A2 >> 8) & 255u;
+    p[2][0] = B & 255u; p[2][1] = (B >> 8) & 255u; p[2][2] = (B >> 16) & 255u;
+    p[3][0] = B >> 24;  p[3][1] = B2 & 255u;       p[3][2] = (B2 >> 8) & 255u;
+    if (BAL) {
+      const int sx0 = (P.tail_start != P.FW) ? (int)((ex % P.pitch) / 3u) : 0;
+#pragma unroll 1
+      for (int t = 0; t < 4; ++t)
+        hsv_roundtrip(p[t][0], p[t][1], p[t][2], delta, (sx0 + (t & 1)) >= P.tail_start, s_hsv, s_hsv + 256);
+    }
+  }
+  const int fx = (ew >> 17) & 31, fy = (ew >> 22) & 31;
+  unsigned ob = (unsigned)bilerp_q10(p[0][0], p[1][0], p[2][0], p[3][0], fx, fy);
+  unsigned og = (unsigned)bilerp_q10(p[0][1], p[1][1], p[2][1], p[3][1], fx, fy);
+  unsigned orr = (unsigned)bilerp_q10(p[0][2], p[1][2], p[2][2], p[3][2], fx, fy);
+  ob = (ob * wm) >> 16; og = (og * wm) >> 16; orr = (orr * wm) >> 16;
+  return ob | (og << 8) | (orr << 16);
+}
+
+// cv2.add of two packed BGR pixels: per-byte saturating add (bytes 0..2; byte 3 stays 0)
+__device__ __forceinline__ unsigned sat_add_bgr(unsigned a, unsigned b) {
+  const unsigned lo = (a & 0x00ff00ffu) + (b & 0x00ff00ffu);          // bytes 0 and 2 -> 9-bit sums in 16-bit lanes
+  const unsigned hi = ((a >> 8) & 0xffu) + ((b >> 8) & 0xffu);        // byte 1
+  const unsigned lo_s = (lo | (((lo >> 8) & 0x00010001u) * 0xffu)) & 0x00ff00ffu;
+  const unsigned hi_s = min(hi, 255u);
+  return lo_s | (hi_s << 8);
+}
+
+// ---- async-copy / mbarrier primitives for the shared-memory source staging ----------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 16-byte asynchronous copy global -> shared, L2 only (SASS: LDGSTS.BYPASS)
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// "count my arrival on the mbarrier once all my earlier cp.async have landed"
+__device__ __forceinline__ void cp_async_arrive(unsigned long long* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+#ifndef BEVK_STAGE_CAP
+#define BEVK_STAGE_CAP 6144        // bytes of one staged source box (one item, one frame-set)
+#endif
+constexpr int STAGE_CAP = BEVK_STAGE_CAP;
+constexpr int STAGE_BOX_BYTES = STAGE_CAP + 64;   // slack: the aligned word loads may run 8 B past the box
+
+// Position in this CTA's walk over units (tile x frame-set group) and their accepted items.
+struct Cursor {
+  long long unit;
+  int it, it_end;
+};
+
+// NB = frame-sets per work unit (1 for single-frame latency, 4 for batches).
+#ifndef BEVK_MIN_CTAS
+#define BEVK_MIN_CTAS 3
+#endif
+template <bool BAL, int NB>
+__global__ void __launch_bounds__(256, BEVK_MIN_CTAS) k_bev(BevParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* boxes = smem_raw;                                                       // [2][NB][STAGE_BOX_BYTES]
+  unsigned* acc = reinterpret_cast<unsigned*>(smem_raw + (P.stage ? 2 * NB * STAGE_BOX_BYTES : 0));   // [NB][ACC_WORDS] BGRX
+  int* s_hsv = reinterpret_cast<int*>(acc + NB * ACC_WORDS);                             // [512] (BALANCE)
+  __shared__ unsigned long long s_sum[BAL ? 3 * NB : 1];
+  __shared__ __align__(8) unsigned long long bar_full[2];
+  const int t = threadIdx.x, lane = t & 31, wrp = t >> 5;
+  if (BAL) {
+    s_hsv[t] = P.hsv_tab[t]; s_hsv[t + 256] = P.hsv_tab[t + 256];
+    if (t < 3 * NB) s_sum[t] = 0ull;
+  }
+  if (t == 0) {
+    mbar_init(&bar_full[0], 256); mbar_init(&bar_full[1], 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const int groups = (P.batch + NB - 1) / NB;
+  const long long n_units = (long long)P.n_tiles * groups;
+  // accumulator word of this thread's first pixel / step to the next one, per orientation
+  const int posx = (wrp * 4) * ACC_WPITCH + lane, stepx = ACC_WPITCH;   // lanes along x, k walks rows
+  const int posy = lane * ACC_WPITCH + wrp * 4, stepy = 1;              // lanes along y, k walks columns
+  __syncthreads();
+
+  // move the cursor to the next accepted item at or after its position (possibly in a later unit)
+  auto settle = [&](Cursor& c) {
+    while (c.unit < n_units) {
+      if (c.it < c.it_end) {
+        const int cam = P.items[c.it].cam;
+        if (cam >= P.cam_lo && cam < P.cam_hi) return;
+        ++c.it;
+      } else {
+        c.unit += gridDim.x;
+        if (c.unit < n_units) {
+          const int4 tl = P.tiles[(int)(c.unit % P.n_tiles)];
+          c.it = tl.z; c.it_end = tl.z + tl.w;
+        }
+      }
+    }
+  };
+  // all threads: start the async copies of that item's source boxes (one per frame-set of the
+  // group) into box set `set`, then register on the set's mbarrier.  Unstaged items only register.
+  auto issue = [&](const Cursor& c, int set) {
+    if (c.unit < n_units) {
+      const BevItem item = P.items[c.it];
+      if (item.staged) {
+        const int b0n = (int)(c.unit / P.n_tiles) * NB, nbn = min(NB, P.batch - b0n);
+        const int cpr = item.row_bytes >> 4;   // 16-byte chunks per box row
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          if (j < nbn) {
+            const uint8_t* s0 = P.srcs[(b0n + j) * P.n_cam + item.cam] + item.src_off;
+            unsigned char* d0 = boxes + (set * NB + j) * STAGE_BOX_BYTES;
+            for (int r = wrp; r < item.rows; r += 8)
+              for (int cix = lane; cix < cpr; cix += 32)
+                cp_async16(d0 + r * item.row_bytes + cix * 16, s0 + (size_t)r * P.pitch + cix * 16);
+          }
+        }
+      }
+    }
+    cp_async_arrive(&bar_full[set]);
+  };
+
+  Cursor la;   // look-ahead: the item whose boxes are being fetched
+  la.unit = blockIdx.x;
+  la.it = la.it_end = 0;
+  if (la.unit < n_units) {
+    const int4 tl = P.tiles[(int)(la.unit % P.n_tiles)];
+    la.it = tl.z; la.it_end = tl.z + tl.w;
+  }
+  settle(la);
+  unsigned n_item = 0;   // accepted items consumed so far: item n uses box set n & 1, mbarrier phase n >> 1
+  if (P.stage) issue(la, 0);
+
+  for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const int tile_id = (int)(unit % P.n_tiles);
+    const int b0 = (int)(unit / P.n_tiles) * NB;
+    const int nb = min(NB, P.batch - b0);
+    const int4 tile = P.tiles[tile_id];
+    __syncthreads();   // previous unit's write-out is done with the accumulator
+    bool first = true;   // no camera has written this tile yet: the first one stores (zeros where masked out)
+    for (int it = tile.z; it < tile.z + tile.w; ++it) {
+      const BevItem item = P.items[it];
+      if (item.cam < P.cam_lo || item.cam >= P.cam_hi) continue;
+      const int set = n_item & 1;
+      if (P.stage) {
+        // here `la` is this very item: advance it and start fetching the NEXT item's boxes into the
+        // other set (free since the barrier that ended the item before this one)
+        ++la.it;
+        settle(la);
+        issue(la, set ^ 1);
+      }
+      const uint4* __restrict__ L = P.lut + (size_t)it * (TILE * TILE) + t;
+      const uint8_t* src[NB];
+      int dl[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int b = b0 + (j < nb ? j : 0);   // j >= nb aliases frame-set b0: computed, never written out
+        src[j] = P.srcs[b * P.n_cam + item.cam];
+        dl[j] = BAL ? P.delta[b * P.n_cam + item.cam] : 0;
+      }
+      const int pos = item.orient ? posy : posx, step = item.orient ? stepy : stepx;
+      const bool staged = P.stage && item.staged;
+      const unsigned char* box0 = boxes + (set * NB) * STAGE_BOX_BYTES;
+      const unsigned row_pitch = staged ? (unsigned)item.row_bytes : P.pitch;
+      uint4 nxt = __ldg(L);
+      if (P.stage) mbar_wait(&bar_full[set], (n_item >> 1) & 1);   // this item's boxes have landed
+#pragma unroll 1
+      for (int k = 0; k < 4; ++k) {
+        const uint4 e = nxt;
+        if (k < 3) nxt = __ldg(L + (k + 1) * 256);   // prefetch the next entry under this one's work
+        unsigned* a = acc + pos + k * step;
+        if (!(e.w & LUT_ACTIVE)) {
+          if (first) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) a[j * ACC_WORDS] = 0u;
+          }
+          continue;
+        }
+        if (e.w & LUT_BORDER) {
+          const SlowGeo geo = {P.pitch, P.FW, P.FH, P.tail_start};
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            unsigned v = sample_slow<BAL>(geo, src[j], e.x, e.w, dl[j], s_hsv);
+            if (!first) v = sat_add_bgr(v, a[j * ACC_WORDS]);
+            a[j * ACC_WORDS] = v;
+          }
+        } else {
+          // phase 1: every tap load of the NB frame-sets in flight before any is consumed;
+          // phase 2: interpolate, weight, accumulate (cv2.add order: front, back, left, right)
+          const unsigned off_al = e.x & ~3u, sh = (e.x & 3u) * 8u, wm = e.w & 0x1ffffu;
+          const bool third = (sh == 24u);
+          unsigned a0[NB], a1[NB], a2[NB], b0w[NB], b1w[NB], b2w[NB];
+          if (staged) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+              const unsigned* q0 = reinterpret_cast<const unsigned*>(box0 + j * STAGE_BOX_BYTES + off_al);
+              const unsigned* q1 = reinterpret_cast<const unsigned*>(box0 + j * STAGE_BOX_BYTES + off_al + row_pitch);
+              a0[j] = q0[0]; a1[j] = q0[1]; a2[j] = third ? q0[2] : 0u;
+              b0w[j] = q1[0]; b1w[j] = q1[1]; b2w[j] = third ? q1[2] : 0u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+              const uint8_t* q0 = src[j] + off_al;
+              const uint8_t* q1 = q0 + P.pitch;
+              a0[j] = ldg32(q0); a1[j] = ldg32(q0 + 4); a2[j] = third ? ldg32(q0 + 8) : 0u;
+              b0w[j] = ldg32(q1); b1w[j] = ldg32(q1 + 4); b2w[j] = third ? ldg32(q1 + 8) : 0u;
+            }
+          }
+          if (BAL) {
+            bool tail0 = false, tail1 = false;
+            if (P.tail_start != P.FW) {   // only frames whose width is not a multiple of 32 have a rounding tail
+              const unsigned xb = staged ? (e.x % row_pitch + (unsigned)item.pad1) : (e.x % P.pitch);
+              const int sx0 = (int)(xb / 3u);
+              tail0 = sx0 >= P.tail_start; tail1 = sx0 + 1 >= P.tail_start;
+            }
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+              unsigned v = interp_bal(sh, e.w, a0[j], a1[j], a2[j], b0w[j], b1w[j], b2w[j], dl[j], tail0, tail1, s_hsv);
+              if (!first) v = sat_add_bgr(v, a[j * ACC_WORDS]);
+              a[j * ACC_WORDS] = v;
+            }
+          } else if (first) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+              a[j * ACC_WORDS] = interp_fast(sh, e.y, e.z, wm, a0[j], a1[j], a2[j], b0w[j], b1w[j], b2w[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+              a[j * ACC_WORDS] =
+                  sat_add_bgr(interp_fast(sh, e.y, e.z, wm, a0[j], a1[j], a2[j], b0w[j], b1w[j], b2w[j]), a[j * ACC_WORDS]);
+          }
+        }
+      }
+      first = false;
+      ++n_item;
+      __syncthreads();   // the next camera may touch the same pixels from other threads; box set is free
+    }
+    // ---- write the tile(s): thread t -> row t/8, 4 pixels (12 bytes) at pixel 4*(t%8) ----
+    const int row = t >> 3, chunk = t & 7;
+    const int gy = tile.y + row, gx = tile.x + chunk * 4;
+    const bool inb = (gy < P.BH) && (gx < P.BW);
+    const size_t pix_off = (size_t)gy * P.BW * 3 + (size_t)gx * 3;
+    const bool full = inb && (gx + 4 <= P.BW) && ((P.BW * 3) % 4 == 0) && (P.canvas_bytes % 4 == 0);
+    const int npx = inb ? min(4, P.BW - gx) : 0;
+    unsigned c0 = 0, c1 = 0, c2 = 0;
+    if (!BAL && P.car && full) {
+      const unsigned* c = reinterpret_cast<const unsigned*>(P.car + pix_off);
+      c0 = __ldg(c); c1 = __ldg(c + 1); c2 = __ldg(c + 2);
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      if (j >= nb) break;
+      const unsigned* a = acc + j * ACC_WORDS + row * ACC_WPITCH + chunk * 4;
+      unsigned x0 = a[0], x1 = a[1], x2 = a[2], x3 = a[3];                 // BGRX BGRX BGRX BGRX
+      if (first) x0 = x1 = x2 = x3 = 0u;                                   // tile without a camera (car hole)
+      unsigned w0 = __byte_perm(x0, x1, 0x4210);                           // B0 G0 R0 B1
+      unsigned w1 = __byte_perm(x1, x2, 0x5421);                           // G1 R1 B2 G2
+      unsigned w2 = __byte_perm(x2, x3, 0x6542);                           // R2 B3 G3 R3
+      if (BAL) {   // channel sums of the composed canvas, before gains and car (surroundBEV.py:44-47)
+        const unsigned px[4] = {x0, x1, x2, x3};
+        unsigned sb = 0, sg = 0, sr = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < npx) { sb += px[q] & 255u; sg += (px[q] >> 8) & 255u; sr += (px[q] >> 16) & 255u; }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {   // every lane takes part (out-of-canvas lanes add 0)
+          sb += __shfl_xor_sync(0xffffffffu, sb, s);
+          sg += __shfl_xor_sync(0xffffffffu, sg, s);
+          sr += __shfl_xor_sync(0xffffffffu, sr, s);
+        }
+        if (lane == 0) {
+          atomicAdd(&s_sum[3 * j + 0], (unsigned long long)sb);
+          atomicAdd(&s_sum[3 * j + 1], (unsigned long long)sg);
+          atomicAdd(&s_sum[3 * j + 2], (unsigned long long)sr);
+        }
+      }
+      if (!inb) continue;
+      uint8_t* o = P.out + (size_t)(b0 + j) * P.canvas_bytes + pix_off;
+      if (full) {
+        if (!BAL && P.car) { w0 = __vaddus4(w0, c0); w1 = __vaddus4(w1, c1); w2 = __vaddus4(w2, c2); }
+        unsigned* g = reinterpret_cast<unsigned*>(o);
+        g[0] = w0; g[1] = w1; g[2] = w2;
+      } else {
+        const unsigned wv[3] = {w0, w1, w2};
+#pragma unroll 1
+        for (int i = 0; i < npx * 3; ++i) {
+          int v = (wv[i >> 2] >> (8 * (i & 3))) & 255u;
+          if (!BAL && P.car) v = min(255, v + P.car[pix_off + i]);
+          o[i] = (uint8_t)v;
+        }
+      }
+    }
+    if (BAL) {
+      __syncthreads();
+      if (t < 3 * nb) { atomicAdd(P.csum + (size_t)(b0 + t / 3) * 3 + (t % 3), s_sum[t]); s_sum[t] = 0ull; }
+    }
+  }
+}
+
+constexpr size_t bev_smem_bytes(bool stage, int nb) {
+  return (stage ? (size_t)2 * nb * STAGE_BOX_BYTES : 0) + (size_t)nb * ACC_WORDS * 4 + 512 * sizeof(int);
+}
+
+}  // namespace bevk
