@@ -403,3 +403,71 @@ def test_blend_weight_all_pixel_mask_pairs(ops):
     want = R.apply_blend(img[:n, :n], mask)
     assert (got == want).all()
     assert (ops.apply_mask(img[:n, :n], mask, blend=True) == want).all()
+
+
+def test_bev_eight_cameras_wedge_masks(ops, fx):
+    """BASELINE configs[4] semantics at a small size: cameras 0-3 = the scaled
+    fixtures, 4-7 = the same four with H post-multiplied by a 45-degree rotation about the canvas
+    centre; 8 angular wedge masks; oracle = the reference's Camera.raw2bev per camera + the N-way
+    saturating compose.  Also exercises camera ranges (camera-per-GPU sharding) on 8 cameras."""
+    g = fx.geometry(640, 512, 480, 480)
+    calib4 = fx.scaled_calib(g)
+    c, s_ = np.cos(np.pi / 4), np.sin(np.pi / 4)
+    cx, cy = g.BW / 2, g.BH / 2
+    Rot = np.array([[c, -s_, cx - c * cx + s_ * cy], [s_, c, cy - s_ * cx - c * cy], [0, 0, 1.0]])
+    cams = [calib4[n] for n in NAMES] + [(calib4[n][0], calib4[n][1], Rot @ calib4[n][2]) for n in NAMES]
+    ang = np.linspace(0, 2 * np.pi, 9)
+    rad = g.BW
+    masks = []
+    for i in range(8):
+        tri = np.array([[cx, cy], [cx + rad * np.cos(ang[i]), cy + rad * np.sin(ang[i])],
+                        [cx + rad * np.cos(ang[i + 1]), cy + rad * np.sin(ang[i + 1])]]).astype(np.int32)
+        masks.append(cv2.fillPoly(np.zeros((g.BH, g.BW), np.uint8), [tri], 255))
+    e = ops.BevEngine(8, (g.FW, g.FH), (g.BW, g.BH))
+    frames = fx.frames(g.FW, g.FH)
+    frames8 = frames + [np.ascontiguousarray(f[:, ::-1]) for f in frames]
+    want = np.zeros((g.BH, g.BW, 3), np.uint8)
+    for i, (K, D, H) in enumerate(cams):
+        e.set_camera(i, K, D, C.dst_camera_matrix(K, g.FW, g.FH, g.FS, g.SS), (int(g.FW * g.SS), int(g.FH * g.SS)), H)
+        e.set_mask(i, masks[i])
+        rc = C.RefCamera(K, D, H, g)
+        want = R.sat_add(want, R.apply_plain(rc.raw2bev(frames8[i]), masks[i]))
+    got = e.run([frames8])[0]
+    assert (got == want).all()
+    import torch
+    dev = torch.device("cuda", e.ctx.device)
+    d = [torch.from_numpy(f).to(dev) for f in frames8]
+    ptrs = torch.tensor([t.data_ptr() for t in d], dtype=torch.int64, device=dev)
+    parts = [torch.empty((g.BH, g.BW, 3), dtype=torch.uint8, device=dev) for _ in range(3)]
+    torch.cuda.synchronize()
+    for p, (lo, hi) in zip(parts, [(0, 3), (3, 6), (6, 8)]):       # ragged camera ranges
+        e.run_device_cams(ptrs.data_ptr(), 1, lo, hi, p.data_ptr())
+    full = torch.empty_like(parts[0])
+    e.sat_sum_device([p.data_ptr() for p in parts], full.numel(), full.data_ptr())
+    e.ctx.sync()
+    assert (full.cpu().numpy() == want).all()
+
+
+def test_bev_batch_sizes_and_host_pipeline(ops, fx):
+    """Batches that exercise every grouping: 1 and 3 (single-frame units), 5 and 9 (groups of 4 with
+    a ragged tail), 19 (three chunks of the two-stream host pipeline, ragged), each frame-set
+    different; every canvas must equal the single-frame-set call."""
+    g = fx.geometry(480, 384, 330, 350)
+    e, _ = _engine(ops, fx, g, blend=True)
+    base = fx.frames(g.FW, g.FH)
+    rng = np.random.default_rng(3)
+    sets = []
+    for i in range(19):
+        sets.append([np.ascontiguousarray(np.roll(f, 7 * i + 3 * c, axis=1) ^ rng.integers(0, 8, f.shape, dtype=np.uint8))
+                     for c, f in enumerate(base)])
+    car = fx.car(g.BW, g.BH)
+    singles = [e.run([s], car)[0].copy() for s in sets]
+    for nb in (1, 3, 5, 9, 19):
+        for balance in (False, True):
+            out = e.run(sets[:nb], car, balance)
+            if not balance:
+                for i in range(nb):
+                    assert (out[i] == singles[i]).all(), (nb, i)
+            else:
+                ref = e.run([sets[nb - 1]], car, True)[0]
+                assert (out[nb - 1] == ref).all(), nb
