@@ -131,10 +131,12 @@ struct bevk_ctx {
   int n_cam = 0, FW = 0, FH = 0, BW = 0, BH = 0;
   BevCam cam[BEVK_MAX_CAMERAS];
   bool planned = false;
-  long long n_tiles = 0, n_items = 0, staged_items = 0, staged_bytes = 0;
+  long long n_tiles = 0, n_items = 0, staged_items = 0, staged_bytes = 0, span_px = 0;
   DevBuf d_tiles, d_items, d_lut, d_hsv;
   int bev_grid[6] = {0, 0, 0, 0, 0, 0};   // resident CTAs of k_bev<BAL, NB>: index = 3*BAL + {NB=1:0, 4:1, 8:2}
   DevBuf d_frames, d_ptrs, d_canvas, d_car, d_vsum, d_delta, d_csum;
+  DevBuf d_spans, d_bal, d_bal_ptrs;        // BALANCE: sampled row spans per camera, balanced frame copies + their table
+  const void* bal_ptrs_for = nullptr; long long bal_ptrs_n = 0;
 };
 
 static int use(bevk_ctx* c) {
@@ -177,7 +179,8 @@ int bevk_ctx_destroy(bevk_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (DevBuf* b : {&c->s_src, &c->s_dst, &c->s_m1, &c->s_m2, &c->s_o1, &c->s_o2, &c->d_tiles, &c->d_items, &c->d_lut,
-                    &c->d_hsv, &c->d_frames, &c->d_ptrs, &c->d_canvas, &c->d_car, &c->d_vsum, &c->d_delta, &c->d_csum})
+                    &c->d_hsv, &c->d_frames, &c->d_ptrs, &c->d_canvas, &c->d_car, &c->d_vsum, &c->d_delta, &c->d_csum,
+                    &c->d_spans, &c->d_bal, &c->d_bal_ptrs})
     b->release();
   for (auto& u : c->und) { u.map1.release(); u.map2.release(); }
   for (auto& k : c->cam) { k.map1.release(); k.map2.release(); }
@@ -522,6 +525,13 @@ int bevk_bev_finalize(bevk_ctx* c) {
   std::vector<uint4> lut;
   tiles.reserve((size_t)tx * ty);
   c->staged_items = 0; c->staged_bytes = 0;
+  // per camera and source row: [first, last+1) column any in-frame tap touches (for k_lum_spans)
+  std::vector<int2> spans((size_t)NC * FH, make_int2(INT_MAX, -1));
+  auto touch = [&](int k, int x, int y) {
+    if (x < 0 || y < 0 || x >= FW || y >= FH) return;
+    int2& sp = spans[(size_t)k * FH + y];
+    sp.x = std::min(sp.x, x); sp.y = std::max(sp.y, x + 1);
+  };
   for (int tj = 0; tj < ty; ++tj)
     for (int ti = 0; ti < tx; ++ti) {
       const int x0 = ti * TILE, y0 = tj * TILE;
@@ -542,6 +552,7 @@ int bevk_bev_finalize(bevk_ctx* c) {
             if (!mk[p]) continue;
             any = true;
             const int sx = m1[k][2 * p], sy = m1[k][2 * p + 1];
+            touch(k, sx, sy); touch(k, sx + 1, sy); touch(k, sx, sy + 1); touch(k, sx + 1, sy + 1);
             if (x + 1 < BW && mk[p + 1]) cx += std::abs(m1[k][2 * (p + 1) + 1] - sy);
             if (y + 1 < BH && mk[p + BW]) cy += std::abs(m1[k][2 * (p + BW) + 1] - sy);
             if (in_frame(sx, sy)) {
@@ -615,6 +626,11 @@ int bevk_bev_finalize(bevk_ctx* c) {
     CU(cudaMemcpyAsync(c->d_items.p, items.data(), items.size() * sizeof(BevItem), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_lut.p, lut.data(), lut.size() * sizeof(uint4), cudaMemcpyHostToDevice, c->stream));
   }
+  for (auto& sp : spans) if (sp.y < 0) sp = make_int2(0, 0);
+  RET(c->d_spans.ensure(spans.size() * sizeof(int2)));
+  CU(cudaMemcpyAsync(c->d_spans.p, spans.data(), spans.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+  c->span_px = 0;
+  for (const auto& sp : spans) c->span_px += sp.y - sp.x;
   // OpenCV's 8-bit HSV division tables (color_hsv: sdiv_table / hdiv_table180, hsv_shift = 12)
   std::vector<int> tab(512, 0);
   for (int i = 1; i < 256; ++i) {
@@ -673,9 +689,7 @@ static int run_device(bevk_ctx* c, const void* d_srcs, int batch, const void* d_
   P.out = reinterpret_cast<uint8_t*>(d_out); P.BW = c->BW; P.BH = c->BH;
   P.canvas_bytes = (long long)c->BW * c->BH * 3;
   P.car = reinterpret_cast<const uint8_t*>(d_car);
-  P.hsv_tab = c->d_hsv.as<int>();
   P.cam_lo = cam_lo; P.cam_hi = cam_hi;
-  P.tail_start = c->FW - (c->FW % 32);
   P.n_tiles = (int)c->n_tiles; P.batch = batch;
   P.stage = 1;
   if (const char* env = getenv("BEVK_STAGE")) P.stage = atoi(env) != 0;   // A/B switch for the TMA source staging
@@ -704,7 +718,22 @@ static int run_device(bevk_ctx* c, const void* d_srcs, int batch, const void* d_
     k_delta<<<(batch + 127) / 128, 128, 0, c->stream>>>(c->d_vsum.as<unsigned long long>(), c->n_cam, batch,
                                                          (double)c->FW * (double)c->FH, c->d_delta.as<int>());
     LAUNCHED(c);
-    P.delta = c->d_delta.as<int>();
+    // luminance_balance once per sampled source pixel into balanced frame copies, then the ordinary
+    // fused gather reads those copies
+    const size_t fpad = ((size_t)frame_bytes + 255) & ~size_t(255);
+    RET(c->d_bal.ensure(fpad * nf));
+    RET(c->d_bal_ptrs.ensure(sizeof(void*) * nf));
+    if (c->bal_ptrs_for != c->d_bal.p || c->bal_ptrs_n != nf) {
+      std::vector<uint8_t*> bp((size_t)nf);
+      for (int i = 0; i < nf; ++i) bp[i] = c->d_bal.as<uint8_t>() + (size_t)i * fpad;
+      CU(cudaMemcpyAsync(c->d_bal_ptrs.p, bp.data(), bp.size() * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+      CU(cudaStreamSynchronize(c->stream));   // bp is a stack-lifetime staging vector
+      c->bal_ptrs_for = c->d_bal.p; c->bal_ptrs_n = nf;
+    }
+    k_lum_spans<<<dim3(c->FH, nf), 128, 0, c->stream>>>(P.srcs, c->d_bal_ptrs.as<uint8_t*>(), c->d_spans.as<int2>(), c->n_cam,
+                                                       c->FW, c->FH, c->d_delta.as<int>(), c->d_hsv.as<int>());
+    LAUNCHED(c);
+    P.srcs = c->d_bal_ptrs.as<const uint8_t*>();
     P.csum = c->d_csum.as<unsigned long long>();
     if (nbu == 8) k_bev<true, 8><<<bev_blocks, 256, bev_smem, c->stream>>>(P);
     else if (nbu == 4) k_bev<true, 4><<<bev_blocks, 256, bev_smem, c->stream>>>(P);

@@ -3,9 +3,9 @@
 // Reference path fused here (SurroundBirdEyeView/surroundBEV.py:312-325): for every
 // camera  raw2bev = cv2.remap(img, bev_map1, bev_map2, INTER_LINEAR)  (:116-117), then
 // Mask / BlendMask.__call__ (:161-162 / :279-280), then the saturating cv2.add chain
-// (:318-320), the optional car overlay (:323-324), and -- in the BALANCE variant --
-// luminance_balance applied lazily to the sampled taps (:57-79) plus the channel sums
-// color_balance needs (:44-47).  No intermediate image is written to HBM.
+// (:318-320), the optional car overlay (:323-324), and -- in the BALANCE variant -- the channel
+// sums color_balance needs (:44-47); luminance_balance (:57-79) has then already been applied
+// to the frames' sampled row spans by k_lum_spans.  No warped intermediate is written to HBM.
 //
 // Work decomposition
 //   * canvas tiles of 32x32 px; per tile a list of "items" = cameras whose mask touches it;
@@ -56,11 +56,8 @@ struct BevParams {
   int n_tiles, batch;
   uint8_t* out; int BW, BH; long long canvas_bytes;
   const uint8_t* car;
-  const int* delta;             // [batch * n_cam] luminance offsets (BALANCE)
   unsigned long long* csum;     // [batch * 3] channel sums of the composed canvas (BALANCE)
-  const int* hsv_tab;           // sdiv[256] ++ hdiv[256]
   int cam_lo, cam_hi;
-  int tail_start;               // FW - FW % 32: first column of OpenCV's scalar HSV2BGR row tail
   int stage;                    // reserved
 };
 
@@ -83,72 +80,24 @@ __device__ __forceinline__ unsigned interp_fast(unsigned sh, unsigned wpx, unsig
   return __byte_perm(__byte_perm(ob * wm, og * wm, 0x0062), orr * wm, 0x7610);
 }
 
-// BALANCE variant of interp_fast: OpenCV's 8-bit BGR -> HSV -> (V + delta) -> BGR round trip
-// (luminance_balance, surroundBEV.py:57-79) on each of the four taps, then the same Q10
-// interpolation and weight.  tail0/tail1: the left/right tap columns lie in OpenCV's rounding row tail.
-__device__ __forceinline__ unsigned interp_bal(unsigned sh, unsigned ew, unsigned a0, unsigned a1, unsigned a2, unsigned b0,
-                                               unsigned b1, unsigned b2, int delta, bool tail0, bool tail1,
-                                               const int* s_hsv) {
-  const unsigned A = __funnelshift_r(a0, a1, sh), A2 = __funnelshift_r(a1, a2, sh);
-  const unsigned B = __funnelshift_r(b0, b1, sh), B2 = __funnelshift_r(b1, b2, sh);
-  int p00b = A & 255u, p00g = (A >> 8) & 255u, p00r = (A >> 16) & 255u;
-  int p01b = A >> 24, p01g = A2 & 255u, p01r = (A2 >> 8) & 255u;
-  int p10b = B & 255u, p10g = (B >> 8) & 255u, p10r = (B >> 16) & 255u;
-  int p11b = B >> 24, p11g = B2 & 255u, p11r = (B2 >> 8) & 255u;
-  hsv_roundtrip(p00b, p00g, p00r, delta, tail0, s_hsv, s_hsv + 256);
-  hsv_roundtrip(p01b, p01g, p01r, delta, tail1, s_hsv, s_hsv + 256);
-  hsv_roundtrip(p10b, p10g, p10r, delta, tail0, s_hsv, s_hsv + 256);
-  hsv_roundtrip(p11b, p11g, p11r, delta, tail1, s_hsv, s_hsv + 256);
-  const int fx = (ew >> 17) & 31, fy = (ew >> 22) & 31;
-  const unsigned wm = ew & 0x1ffffu;
-  const unsigned ob = (unsigned)bilerp_q10(p00b, p01b, p10b, p11b, fx, fy);
-  const unsigned og = (unsigned)bilerp_q10(p00g, p01g, p10g, p11g, fx, fy);
-  const unsigned orr = (unsigned)bilerp_q10(p00r, p01r, p10r, p11r, fx, fy);
-  return __byte_perm(__byte_perm(ob * wm, og * wm, 0x0062), orr * wm, 0x7610);
-}
-
 // Slow path (kept out of line so the hot loop stays inside the instruction cache): entries with
 // out-of-frame taps (BORDER_CONSTANT 0 per tap; also every entry when the pitch is not a multiple
-// of 4) and the BALANCE variant, which runs OpenCV's 8-bit HSV round trip on each of the four taps.
-struct SlowGeo { unsigned pitch; int FW, FH, tail_start; };
-template <bool BAL>
-__device__ __noinline__ unsigned sample_slow(const SlowGeo P, const uint8_t* __restrict__ src, unsigned ex, unsigned ew,
-                                             int delta, const int* s_hsv) {
+// of 4).
+struct SlowGeo { unsigned pitch; int FW, FH; };
+__device__ __noinline__ unsigned sample_slow(const SlowGeo P, const uint8_t* __restrict__ src, unsigned ex, unsigned ew) {
   int p[4][3];
   const unsigned wm = ew & 0x1ffffu;
-  if (ew & LUT_BORDER) {
-    const int sx = (short)(ex & 0xffffu), sy = (short)(ex >> 16);
+  const int sx = (short)(ex & 0xffffu), sy = (short)(ex >> 16);
 #pragma unroll 1
-    for (int t = 0; t < 4; ++t) {
-      const int tx = sx + (t & 1), ty = sy + (t >> 1);
-      const bool in = ((unsigned)tx < (unsigned)P.FW) && ((unsigned)ty < (unsigned)P.FH);
-      int c0 = 0, c1 = 0, c2 = 0;
-      if (in) {
-        const uint8_t* q = src + (size_t)ty * P.pitch + 3 * tx;
-        c0 = __ldg(q); c1 = __ldg(q + 1); c2 = __ldg(q + 2);
-        if (BAL) hsv_roundtrip(c0, c1, c2, delta, tx >= P.tail_start, s_hsv, s_hsv + 256);
-      }   // else: the border constant is not an image pixel, no balance
-      p[t][0] = c0; p[t][1] = c1; p[t][2] = c2;
+  for (int t = 0; t < 4; ++t) {
+    const int tx = sx + (t & 1), ty = sy + (t >> 1);
+    const bool in = ((unsigned)tx < (unsigned)P.FW) && ((unsigned)ty < (unsigned)P.FH);
+    int c0 = 0, c1 = 0, c2 = 0;
+    if (in) {
+      const uint8_t* q = src + (size_t)ty * P.pitch + 3 * tx;
+      c0 = __ldg(q); c1 = __ldg(q + 1); c2 = __ldg(q + 2);
     }
-  } else {
-    const unsigned off_al = ex & ~3u, sh = (ex & 3u) * 8u;
-    const uint8_t* q0 = src + off_al;
-    const uint8_t* q1 = q0 + P.pitch;
-    const bool third = (sh == 24u);
-    const unsigned a0 = ldg32(q0), a1 = ldg32(q0 + 4), a2 = third ? ldg32(q0 + 8) : 0u;
-    const unsigned b0 = ldg32(q1), b1 = ldg32(q1 + 4), b2 = third ? ldg32(q1 + 8) : 0u;
-    const unsigned A = __funnelshift_r(a0, a1, sh), A2 = __funnelshift_r(a1, a2, sh);
-    const unsigned B = __funnelshift_r(b0, b1, sh), B2 = __funnelshift_r(b1, b2, sh);
-    p[0][0] = A & 255u; p[0][1] = (A >> 8) & 255u; p[0][2] = (A >> 16) & 255u;
-    p[1][0] = A >> 24;  p[1][1] = A2 & 255u;       p[1][2] = (A2 >> 8) & 255u;
-    p[2][0] = B & 255u; p[2][1] = (B >> 8) & 255u; p[2][2] = (B >> 16) & 255u;
-    p[3][0] = B >> 24;  p[3][1] = B2 & 255u;       p[3][2] = (B2 >> 8) & 255u;
-    if (BAL) {
-      const int sx0 = (P.tail_start != P.FW) ? (int)((ex % P.pitch) / 3u) : 0;
-#pragma unroll 1
-      for (int t = 0; t < 4; ++t)
-        hsv_roundtrip(p[t][0], p[t][1], p[t][2], delta, (sx0 + (t & 1)) >= P.tail_start, s_hsv, s_hsv + 256);
-    }
+    p[t][0] = c0; p[t][1] = c1; p[t][2] = c2;
   }
   const int fx = (ew >> 17) & 31, fy = (ew >> 22) & 31;
   unsigned ob = (unsigned)bilerp_q10(p[0][0], p[1][0], p[2][0], p[3][0], fx, fy);
@@ -175,13 +124,9 @@ template <bool BAL, int NB>
 __global__ void __launch_bounds__(256, BEVK_MIN_CTAS) k_bev(BevParams P) {
   extern __shared__ __align__(16) unsigned smem_w[];
   unsigned* acc = smem_w;                                   // [NB][ACC_WORDS] packed BGRX
-  int* s_hsv = reinterpret_cast<int*>(smem_w + NB * ACC_WORDS);   // [512] (BALANCE)
   __shared__ unsigned long long s_sum[BAL ? 3 * NB : 1];
   const int t = threadIdx.x, lane = t & 31, wrp = t >> 5;
-  if (BAL) {
-    s_hsv[t] = P.hsv_tab[t]; s_hsv[t + 256] = P.hsv_tab[t + 256];
-    if (t < 3 * NB) s_sum[t] = 0ull;
-  }
+  if (BAL && t < 3 * NB) s_sum[t] = 0ull;
   const int groups = (P.batch + NB - 1) / NB;
   const long long n_units = (long long)P.n_tiles * groups;
   // accumulator word of this thread's first pixel / step to the next one, per orientation
@@ -200,12 +145,10 @@ __global__ void __launch_bounds__(256, BEVK_MIN_CTAS) k_bev(BevParams P) {
       if (item.cam < P.cam_lo || item.cam >= P.cam_hi) continue;
       const uint4* __restrict__ L = P.lut + (size_t)it * (TILE * TILE) + t;
       const uint8_t* src[NB];
-      int dl[NB];
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         const int b = b0 + (j < nb ? j : 0);   // j >= nb aliases frame-set b0: computed, never written out
         src[j] = P.srcs[b * P.n_cam + item.cam];
-        dl[j] = BAL ? P.delta[b * P.n_cam + item.cam] : 0;
       }
       const int pos = item.orient ? posy : posx, step = item.orient ? stepy : stepx;
       uint4 nxt = __ldg(L);
@@ -222,10 +165,10 @@ __global__ void __launch_bounds__(256, BEVK_MIN_CTAS) k_bev(BevParams P) {
           continue;
         }
         if (e.w & LUT_BORDER) {
-          const SlowGeo geo = {P.pitch, P.FW, P.FH, P.tail_start};
+          const SlowGeo geo = {P.pitch, P.FW, P.FH};
 #pragma unroll
           for (int j = 0; j < NB; ++j) {
-            unsigned v = sample_slow<BAL>(geo, src[j], e.x, e.w, dl[j], s_hsv);
+            unsigned v = sample_slow(geo, src[j], e.x, e.w);
             if (!first) v = sat_add_bgr(v, a[j * ACC_WORDS]);
             a[j * ACC_WORDS] = v;
           }
@@ -242,19 +185,7 @@ __global__ void __launch_bounds__(256, BEVK_MIN_CTAS) k_bev(BevParams P) {
             a0[j] = ldg32(q0); a1[j] = ldg32(q0 + 4); a2[j] = third ? ldg32(q0 + 8) : 0u;
             b0w[j] = ldg32(q1); b1w[j] = ldg32(q1 + 4); b2w[j] = third ? ldg32(q1 + 8) : 0u;
           }
-          if (BAL) {
-            bool tail0 = false, tail1 = false;
-            if (P.tail_start != P.FW) {   // only frames whose width is not a multiple of 32 have a rounding tail
-              const int sx0 = (int)((e.x % P.pitch) / 3u);
-              tail0 = sx0 >= P.tail_start; tail1 = sx0 + 1 >= P.tail_start;
-            }
-#pragma unroll
-            for (int j = 0; j < NB; ++j) {
-              unsigned v = interp_bal(sh, e.w, a0[j], a1[j], a2[j], b0w[j], b1w[j], b2w[j], dl[j], tail0, tail1, s_hsv);
-              if (!first) v = sat_add_bgr(v, a[j * ACC_WORDS]);
-              a[j * ACC_WORDS] = v;
-            }
-          } else if (first) {
+          if (first) {
 #pragma unroll
             for (int j = 0; j < NB; ++j)
               a[j * ACC_WORDS] = interp_fast(sh, e.y, e.z, wm, a0[j], a1[j], a2[j], b0w[j], b1w[j], b2w[j]);
@@ -331,6 +262,6 @@ __global__ void __launch_bounds__(256, BEVK_MIN_CTAS) k_bev(BevParams P) {
   }
 }
 
-constexpr size_t bev_smem_bytes(bool /*bal*/, int nb) { return (size_t)nb * ACC_WORDS * 4 + 512 * sizeof(int); }
+constexpr size_t bev_smem_bytes(bool /*bal*/, int nb) { return (size_t)nb * ACC_WORDS * 4; }
 
 }  // namespace bevk

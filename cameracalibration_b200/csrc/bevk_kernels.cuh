@@ -424,4 +424,30 @@ __global__ void __launch_bounds__(256) k_lum_apply(const uint8_t* const* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------
+// K8 part 3 for the fused BEV path: luminance_balance applied ONCE to every source pixel the LUT
+// can sample.  spans[cam * FH + y] = (first, last+1) source column of row y that any tap of camera
+// `cam` touches (bevk_bev_finalize); everything else in the frame is never read by k_bev, so it
+// is not converted (about 17 % of a frame at the fixture geometry, 4.6x fewer HSV round trips
+// than converting the four taps of every output pixel).  grid = (FH, n_frames).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_lum_spans(const uint8_t* const* __restrict__ frames, uint8_t* const* __restrict__ outs,
+                                                   const int2* __restrict__ spans, int n_cam, int w, int h,
+                                                   const int* __restrict__ delta, const int* __restrict__ hsv_tab) {
+  const int y = blockIdx.x, f = blockIdx.y;
+  const int2 sp = spans[(f % n_cam) * h + y];
+  if (sp.y <= sp.x) return;
+  __shared__ int s_tab[512];
+  for (int i = threadIdx.x; i < 512; i += 128) s_tab[i] = hsv_tab[i];
+  __syncthreads();
+  const uint8_t* src = frames[f] + (size_t)y * w * 3;
+  uint8_t* dst = outs[f] + (size_t)y * w * 3;
+  const int d = delta[f], tail = w - (w % 32);
+  for (int x = sp.x + threadIdx.x; x < sp.y; x += 128) {
+    int b = src[3 * x], g = src[3 * x + 1], r = src[3 * x + 2];
+    hsv_roundtrip(b, g, r, d, x >= tail, s_tab, s_tab + 256);
+    dst[3 * x] = (uint8_t)b; dst[3 * x + 1] = (uint8_t)g; dst[3 * x + 2] = (uint8_t)r;
+  }
+}
+
 }  // namespace bevk
