@@ -157,7 +157,12 @@ class Camera:
         g = self._g
         if img.dtype == np.uint8:
             return ops.warp_perspective(img, self.homography, (g.BW, g.BH))
-        raise L.BevkError("warp_homography: uint8 images only (map planes go through Camera.get_bev_maps)")
+        # the reference also pushes the undistortion map planes through this method (get_bev_maps)
+        if img.dtype == np.int16 and img.ndim == 3 and img.shape[2] == 2:
+            return ops.warp_perspective_maps(img, np.zeros(img.shape[:2], np.uint16), self.homography, (g.BW, g.BH))[0]
+        if img.dtype == np.uint16 and img.ndim == 2:
+            return ops.warp_perspective_maps(np.zeros(img.shape + (2,), np.int16), img, self.homography, (g.BW, g.BH))[1]
+        raise L.BevkError("warp_homography: uint8 images or CV_16SC2 / CV_16UC1 map planes only")
 
     def raw2bev(self, img):
         return self._single().run([[img]])[0]

@@ -132,6 +132,7 @@ struct bevk_ctx {
   BevCam cam[BEVK_MAX_CAMERAS];
   bool planned = false;
   long long n_tiles = 0, n_items = 0, staged_items = 0, staged_bytes = 0, span_px = 0;
+  int nb_override = 0;   // BEVK_NB tuning override, read at finalize
   DevBuf d_tiles, d_items, d_lut, d_hsv;
   int bev_grid[6] = {0, 0, 0, 0, 0, 0};   // resident CTAs of k_bev<BAL, NB>: index = 3*BAL + {NB=1:0, 4:1, 8:2}
   DevBuf d_frames, d_ptrs, d_canvas, d_car, d_vsum, d_delta, d_csum;
@@ -525,6 +526,11 @@ int bevk_bev_finalize(bevk_ctx* c) {
   std::vector<uint4> lut;
   tiles.reserve((size_t)tx * ty);
   c->staged_items = 0; c->staged_bytes = 0;
+  c->nb_override = 0;
+  if (const char* env = getenv("BEVK_NB")) {   // tuning override of the frame-sets per work unit: 1, 4 or 8
+    const int v = atoi(env);
+    if (v == 1 || v == 4 || v == 8) c->nb_override = v;
+  }
   // per camera and source row: [first, last+1) column any in-frame tap touches (for k_lum_spans)
   std::vector<int2> spans((size_t)NC * FH, make_int2(INT_MAX, -1));
   auto touch = [&](int k, int x, int y) {
@@ -695,10 +701,7 @@ static int run_device(bevk_ctx* c, const void* d_srcs, int batch, const void* d_
   if (const char* env = getenv("BEVK_STAGE")) P.stage = atoi(env) != 0;   // A/B switch for the TMA source staging
   // frame-sets per work unit: 4 amortises the LUT decode over a batch; 1 for single frames
   int nbu = batch >= 4 ? 4 : 1;
-  if (const char* env = getenv("BEVK_NB")) {   // tuning override: 1, 4 or 8
-    const int v = atoi(env);
-    if (v == 1 || v == 4 || v == 8) nbu = v;
-  }
+  if (c->nb_override) nbu = c->nb_override;
   const long long units = c->n_tiles * ((batch + nbu - 1) / nbu);
   const int variant = (bal ? 3 : 0) + (nbu == 8 ? 2 : (nbu == 4 ? 1 : 0));
   const unsigned bev_blocks = (unsigned)std::max<long long>(1, std::min<long long>(units, c->bev_grid[variant]));

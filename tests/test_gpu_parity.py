@@ -325,6 +325,9 @@ def test_dropin_bevgenerator_classes(fx, tmp_path):
     assert h16(u) == gold["undistort"]
     assert h16(cam.warp_homography(u)) == gold["warp_undistort"]
     assert (h16(cam.bev_maps[0]), h16(cam.undistort_maps[1])) == (gold["bev_map1"], gold["und_map2"])
+    # the reference's own way to the BEV maps: warp_homography applied to each undistort-map plane
+    assert h16(cam.warp_homography(cam.undistort_maps[0])) == gold["bev_map1"]
+    assert h16(cam.warp_homography(cam.undistort_maps[1])) == gold["bev_map2"]
     plain = S.Mask("front")
     assert h16(plain.mask) == fx.gold["mask_plain"]["front"]
     w = cam.raw2bev(F[2])
