@@ -340,6 +340,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * nb * n_e2e / float(te.item())   # e2e always runs the frames policy (each rank its own batch)
     same = bool((torch.from_numpy(np.asarray(pin_out)).to(dev) == d_out).all().item())
+    h2d_set, d2h_set = eng.host_copy_bytes(w["balance"])   # bytes bevk_bev_run actually moves per frame-set
 
     if rank == 0:
         peaks = {}
@@ -363,9 +364,10 @@ def main():
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
                 "ms_per_step": ms_all / a.steps, "higher_is_better": True, "scaling": "strong" if cams else "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic", "config": config,
-                "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": nb * nc * fbytes,
-                        "d2h_bytes_per_step": nb * w["BW"] * w["BH"] * 3, "steps": n_e2e,
-                        "api": "BevEngine.run (ctypes -> bevk_bev_run), pinned host frames", "matches_device_path": same},
+                "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": nb * h2d_set,
+                        "d2h_bytes_per_step": nb * d2h_set, "steps": n_e2e, "frame_bytes_per_step": nb * nc * fbytes,
+                        "api": "BevEngine.run (ctypes -> bevk_bev_run), pinned host frames; without balance only the "
+                               "rectangle of each frame its camera's LUT can sample is uploaded", "matches_device_path": same},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "kernel": "k_bev<false,4>", "kernel_ms": launch_ms,

@@ -133,6 +133,7 @@ struct bevk_ctx {
   bool planned = false;
   long long n_tiles = 0, n_items = 0, staged_items = 0, staged_bytes = 0, span_px = 0;
   int nb_override = 0;   // BEVK_NB tuning override, read at finalize
+  int cam_box[BEVK_MAX_CAMERAS][4] = {};   // per camera: sampled rows [y0,y1), bytes [bx0,bx1)
   DevBuf d_tiles, d_items, d_lut, d_hsv;
   int bev_grid[6] = {0, 0, 0, 0, 0, 0};   // resident CTAs of k_bev<BAL, NB>: index = 3*BAL + {NB=1:0, 4:1, 8:2}
   DevBuf d_frames, d_ptrs, d_canvas, d_car, d_vsum, d_delta, d_csum;
@@ -637,6 +638,21 @@ int bevk_bev_finalize(bevk_ctx* c) {
   CU(cudaMemcpyAsync(c->d_spans.p, spans.data(), spans.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
   c->span_px = 0;
   for (const auto& sp : spans) c->span_px += sp.y - sp.x;
+  // bounding rectangle of the sampled region per camera: the host path uploads only this part of a
+  // frame when the whole frame is not needed (i.e. without BALANCE, whose V means cover the full frame)
+  for (int k = 0; k < NC; ++k) {
+    int y0 = FH, y1 = 0, x0 = FW, x1 = 0;
+    for (int y = 0; y < FH; ++y) {
+      const int2 sp = spans[(size_t)k * FH + y];
+      if (sp.y <= sp.x) continue;
+      y0 = std::min(y0, y); y1 = std::max(y1, y + 1);
+      x0 = std::min(x0, sp.x); x1 = std::max(x1, sp.y);
+    }
+    if (y1 <= y0) { y0 = y1 = x0 = x1 = 0; }
+    // the fast path reads whole aligned words around the taps: widen by 4 px each side (never sampled, only touched)
+    x0 = std::max(0, x0 - 4); x1 = std::min(FW, x1 + 4);
+    c->cam_box[k][0] = y0; c->cam_box[k][1] = y1; c->cam_box[k][2] = x0 * 3; c->cam_box[k][3] = x1 * 3;
+  }
   // OpenCV's 8-bit HSV division tables (color_hsv: sdiv_table / hdiv_table180, hsv_shift = 12)
   std::vector<int> tab(512, 0);
   for (int i = 1; i < 256; ++i) {
@@ -670,6 +686,18 @@ int bevk_bev_plan_info(bevk_ctx* c, int64_t* n_tiles, int64_t* n_items, int64_t*
   if (n_tiles) *n_tiles = c->n_tiles;
   if (n_items) *n_items = c->n_items;
   if (lut_bytes) *lut_bytes = c->n_items * TILE * TILE * (int64_t)sizeof(uint4);
+  return BEVK_OK;
+}
+
+int bevk_bev_host_copy_bytes(bevk_ctx* c, int flags, int64_t* h2d, int64_t* d2h) {
+  RET(use(c));
+  if (!c->planned) return fail(BEVK_ERR_ARG, "bevk_bev_finalize not called");
+  int64_t up = 0;
+  for (int k = 0; k < c->n_cam; ++k)
+    up += (flags & BEVK_FLAG_BALANCE) ? (int64_t)c->FW * c->FH * 3
+                                      : (int64_t)(c->cam_box[k][1] - c->cam_box[k][0]) * (c->cam_box[k][3] - c->cam_box[k][2]);
+  if (h2d) *h2d = up;
+  if (d2h) *d2h = (int64_t)c->BW * c->BH * 3;
   return BEVK_OK;
 }
 
@@ -834,8 +862,15 @@ int bevk_bev_run(bevk_ctx* c, const uint8_t* const* srcs, int64_t src_stride, in
       const uint8_t* s = srcs[(size_t)b0 * c->n_cam + i];
       if (!s) return fail(BEVK_ERR_ARG, "null frame pointer %d", b0 * c->n_cam + i);
       uint8_t* d = dframes + (size_t)i * fpad;
-      if ((size_t)src_stride == row) CU(cudaMemcpyAsync(d, s, fbytes, cudaMemcpyHostToDevice, c->copy_stream));
-      else CU(cudaMemcpy2DAsync(d, row, s, (size_t)src_stride, row, c->FH, cudaMemcpyHostToDevice, c->copy_stream));
+      if (flags & BEVK_FLAG_BALANCE) {   // luminance_balance averages V over the whole raw frame: everything goes up
+        if ((size_t)src_stride == row) CU(cudaMemcpyAsync(d, s, fbytes, cudaMemcpyHostToDevice, c->copy_stream));
+        else CU(cudaMemcpy2DAsync(d, row, s, (size_t)src_stride, row, c->FH, cudaMemcpyHostToDevice, c->copy_stream));
+      } else {                           // only the rectangle of the frame this camera's LUT can sample
+        const int* bx = c->cam_box[i % c->n_cam];
+        if (bx[1] > bx[0])
+          CU(cudaMemcpy2DAsync(d + (size_t)bx[0] * row + bx[2], row, s + (size_t)bx[0] * src_stride + bx[2], (size_t)src_stride,
+                               (size_t)(bx[3] - bx[2]), (size_t)(bx[1] - bx[0]), cudaMemcpyHostToDevice, c->copy_stream));
+      }
     }
     CU(cudaEventRecord(c->ev_in[half], c->copy_stream));
     CU(cudaStreamWaitEvent(c->stream, c->ev_in[half], 0));

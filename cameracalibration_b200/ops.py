@@ -243,6 +243,14 @@ class BevEngine:
                                           L.vptr(out)))
         return out
 
+    def host_copy_bytes(self, balance: bool = False):
+        """(host->device, device->host) bytes per frame-set that run() moves over PCIe."""
+        if not self.finalized:
+            self.finalize()
+        a, b = C.c_int64(), C.c_int64()
+        L.check(self.ctx.lib.bevk_bev_host_copy_bytes(self.ctx.h, L.FLAG_BALANCE if balance else 0, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def _conform(self, f: np.ndarray) -> np.ndarray:
         """The reference never validates frame sizes (cv2.remap samples whatever it is given,
         zero outside).  The engine's LUT is compiled for FW x FH, so other sizes are embedded

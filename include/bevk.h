@@ -146,6 +146,10 @@ int bevk_luminance_balance(bevk_ctx *ctx, const uint8_t *const *imgs, int n, int
 
 /* Introspection for tests / bench */
 int bevk_bev_plan_info(bevk_ctx *ctx, int64_t *n_tiles, int64_t *n_items, int64_t *lut_bytes);
+/* Bytes bevk_bev_run moves over PCIe per frame-set for the given flags: host->device (without
+ * BALANCE only the rectangle of each frame its camera's LUT can sample is uploaded; with BALANCE
+ * the whole frames, because the V means cover them) and device->host (the canvas). */
+int bevk_bev_host_copy_bytes(bevk_ctx *ctx, int flags, int64_t *h2d_per_frame_set, int64_t *d2h_per_frame_set);
 /* Items whose source box is staged in shared memory by TMA, and the bytes those boxes
  * move per frame-set (the rest of the items gather straight from global memory). */
 int bevk_bev_stage_info(bevk_ctx *ctx, int64_t *staged_items, int64_t *staged_bytes_per_frame_set);
