@@ -340,7 +340,8 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * nb * n_e2e / float(te.item())   # e2e always runs the frames policy (each rank its own batch)
     same = bool((torch.from_numpy(np.asarray(pin_out)).to(dev) == d_out).all().item())
-    h2d_set, d2h_set = eng.host_copy_bytes(w["balance"])   # bytes bevk_bev_run actually moves per frame-set
+    _, d2h_set = eng.host_copy_bytes(w["balance"])
+    h2d_set = eng.last_h2d_bytes() // nb                    # bytes the last bevk_bev_run call actually moved, per frame-set
 
     if rank == 0:
         peaks = {}
@@ -367,7 +368,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": nb * h2d_set,
                         "d2h_bytes_per_step": nb * d2h_set, "steps": n_e2e, "frame_bytes_per_step": nb * nc * fbytes,
                         "api": "BevEngine.run (ctypes -> bevk_bev_run), pinned host frames; without balance only the "
-                               "rectangle of each frame its camera's LUT can sample is uploaded", "matches_device_path": same},
+                               "row spans of each frame its camera's LUT can sample cross PCIe (k_fetch_spans)", "matches_device_path": same},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "kernel": "k_bev<false,4>", "kernel_ms": launch_ms,

@@ -20,6 +20,8 @@
 
 using namespace bevk;
 
+#define BEVK_MAX_BANDS 8
+
 // ------------------------------------------------------------------ errors
 static thread_local std::string g_err;
 static int fail(int code, const char* fmt, ...) {
@@ -133,7 +135,14 @@ struct bevk_ctx {
   bool planned = false;
   long long n_tiles = 0, n_items = 0, staged_items = 0, staged_bytes = 0, span_px = 0;
   int nb_override = 0;   // BEVK_NB tuning override, read at finalize
-  int cam_box[BEVK_MAX_CAMERAS][4] = {};   // per camera: sampled rows [y0,y1), bytes [bx0,bx1)
+  int n_bands = 1;
+  bool zero_copy_ok = true;                 // BEVK_ZEROCOPY=0 forces the DMA path
+  DevBuf d_hptrs;                           // device copy of the mapped host frame pointers (per half)
+  const uint8_t** h_hptrs = nullptr;        // pinned staging of those pointers
+  cudaEvent_t ev_hp[2] = {nullptr, nullptr};
+  long long span_fetch_bytes = 0;           // bytes k_fetch_spans moves per frame-set
+  long long last_h2d_bytes = 0;             // host->device bytes of the last bevk_bev_run call
+  int cam_box[BEVK_MAX_CAMERAS][BEVK_MAX_BANDS][4] = {};   // per camera and band: sampled rows [y0,y1), bytes [bx0,bx1)
   DevBuf d_tiles, d_items, d_lut, d_hsv;
   int bev_grid[6] = {0, 0, 0, 0, 0, 0};   // resident CTAs of k_bev<BAL, NB>: index = 3*BAL + {NB=1:0, 4:1, 8:2}
   DevBuf d_frames, d_ptrs, d_canvas, d_car, d_vsum, d_delta, d_csum;
@@ -190,7 +199,9 @@ int bevk_ctx_destroy(bevk_ctx* c) {
   cudaEventDestroy(c->ev1);
   if (c->copy_stream) {
     cudaStreamSynchronize(c->copy_stream);
-    for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_free[i]); }
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_free[i]); cudaEventDestroy(c->ev_hp[i]); }
+    if (c->h_hptrs) cudaFreeHost(c->h_hptrs);
+    c->d_hptrs.release();
     cudaStreamDestroy(c->copy_stream);
   }
   cudaStreamDestroy(c->own);
@@ -638,20 +649,36 @@ int bevk_bev_finalize(bevk_ctx* c) {
   CU(cudaMemcpyAsync(c->d_spans.p, spans.data(), spans.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
   c->span_px = 0;
   for (const auto& sp : spans) c->span_px += sp.y - sp.x;
-  // bounding rectangle of the sampled region per camera: the host path uploads only this part of a
-  // frame when the whole frame is not needed (i.e. without BALANCE, whose V means cover the full frame)
+  // Sampled region per camera as a few horizontal bands, each with its own byte range: the host path
+  // uploads only these rectangles of a frame when the whole frame is not needed (i.e. without BALANCE,
+  // whose V means cover the full frame).  The footprint of a fisheye camera under a BEV mask is
+  // fan-shaped: two bands already cut the plain bounding box from 34 % to 23 % of the frame.
+  c->zero_copy_ok = true;
+  if (const char* env = getenv("BEVK_ZEROCOPY")) c->zero_copy_ok = atoi(env) != 0;
+  c->span_fetch_bytes = 0;
+  for (const auto& sp : spans)
+    if (sp.y > sp.x) c->span_fetch_bytes += std::min<int>(FW * 3, (3 * sp.y + 12 + 15) & ~15) - (std::max(0, 3 * sp.x - 12) & ~15);
+  c->n_bands = 2;
+  if (const char* env = getenv("BEVK_BANDS")) c->n_bands = std::max(1, std::min(BEVK_MAX_BANDS, atoi(env)));
   for (int k = 0; k < NC; ++k) {
-    int y0 = FH, y1 = 0, x0 = FW, x1 = 0;
-    for (int y = 0; y < FH; ++y) {
-      const int2 sp = spans[(size_t)k * FH + y];
-      if (sp.y <= sp.x) continue;
-      y0 = std::min(y0, y); y1 = std::max(y1, y + 1);
-      x0 = std::min(x0, sp.x); x1 = std::max(x1, sp.y);
+    int y0 = FH, y1 = 0;
+    for (int y = 0; y < FH; ++y)
+      if (spans[(size_t)k * FH + y].y > spans[(size_t)k * FH + y].x) { y0 = std::min(y0, y); y1 = std::max(y1, y + 1); }
+    for (int bnd = 0; bnd < c->n_bands; ++bnd) {
+      int* bx = c->cam_box[k][bnd];
+      bx[0] = bx[1] = bx[2] = bx[3] = 0;
+      if (y1 <= y0) continue;
+      const int ya = y0 + (int)((long long)(y1 - y0) * bnd / c->n_bands), yb = y0 + (int)((long long)(y1 - y0) * (bnd + 1) / c->n_bands);
+      int x0 = FW, x1 = 0;
+      for (int y = ya; y < yb; ++y) {
+        const int2 sp = spans[(size_t)k * FH + y];
+        if (sp.y > sp.x) { x0 = std::min(x0, sp.x); x1 = std::max(x1, sp.y); }
+      }
+      if (x1 <= x0 || yb <= ya) continue;
+      // the fast path reads whole aligned words around the taps: widen by 4 px each side (touched, never sampled)
+      x0 = std::max(0, x0 - 4); x1 = std::min(FW, x1 + 4);
+      bx[0] = ya; bx[1] = yb; bx[2] = x0 * 3; bx[3] = x1 * 3;
     }
-    if (y1 <= y0) { y0 = y1 = x0 = x1 = 0; }
-    // the fast path reads whole aligned words around the taps: widen by 4 px each side (never sampled, only touched)
-    x0 = std::max(0, x0 - 4); x1 = std::min(FW, x1 + 4);
-    c->cam_box[k][0] = y0; c->cam_box[k][1] = y1; c->cam_box[k][2] = x0 * 3; c->cam_box[k][3] = x1 * 3;
   }
   // OpenCV's 8-bit HSV division tables (color_hsv: sdiv_table / hdiv_table180, hsv_shift = 12)
   std::vector<int> tab(512, 0);
@@ -689,13 +716,17 @@ int bevk_bev_plan_info(bevk_ctx* c, int64_t* n_tiles, int64_t* n_items, int64_t*
   return BEVK_OK;
 }
 
+int64_t bevk_bev_last_h2d_bytes(bevk_ctx* c) { return c ? c->last_h2d_bytes : 0; }
+
 int bevk_bev_host_copy_bytes(bevk_ctx* c, int flags, int64_t* h2d, int64_t* d2h) {
   RET(use(c));
   if (!c->planned) return fail(BEVK_ERR_ARG, "bevk_bev_finalize not called");
   int64_t up = 0;
-  for (int k = 0; k < c->n_cam; ++k)
-    up += (flags & BEVK_FLAG_BALANCE) ? (int64_t)c->FW * c->FH * 3
-                                      : (int64_t)(c->cam_box[k][1] - c->cam_box[k][0]) * (c->cam_box[k][3] - c->cam_box[k][2]);
+  for (int k = 0; k < c->n_cam; ++k) {
+    if (flags & BEVK_FLAG_BALANCE) { up += (int64_t)c->FW * c->FH * 3; continue; }
+    for (int bnd = 0; bnd < c->n_bands; ++bnd)
+      up += (int64_t)(c->cam_box[k][bnd][1] - c->cam_box[k][bnd][0]) * (c->cam_box[k][bnd][3] - c->cam_box[k][bnd][2]);
+  }
   if (h2d) *h2d = up;
   if (d2h) *d2h = (int64_t)c->BW * c->BH * 3;
   return BEVK_OK;
@@ -826,7 +857,8 @@ int bevk_bev_run(bevk_ctx* c, const uint8_t* const* srcs, int64_t src_stride, in
   // Two-deep pipeline over chunks of frame-sets: the H2D copies of chunk i+1 run on the copy
   // stream while chunk i is rendered and its canvases go back on the main stream, so the two
   // PCIe directions overlap and the kernel hides under the copies.
-  const int chunk = std::min(batch, 8);
+  int chunk = std::min(batch, 4);   // 4 frame-sets = one kernel work group; finer chunks shorten pipeline fill / drain
+  if (const char* env = getenv("BEVK_CHUNK")) chunk = std::max(1, std::min(std::min(batch, 8), atoi(env)));
   const size_t set_frames = (size_t)c->n_cam;
   RET(c->d_frames.ensure(fpad * set_frames * chunk * 2));
   RET(c->d_ptrs.ensure(sizeof(void*) * set_frames * chunk * 2));
@@ -836,6 +868,7 @@ int bevk_bev_run(bevk_ctx* c, const uint8_t* const* srcs, int64_t src_stride, in
     for (int i = 0; i < 2; ++i) {
       CU(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
       CU(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&c->ev_hp[i], cudaEventDisableTiming));
     }
   }
   if (car) {
@@ -854,22 +887,63 @@ int bevk_bev_run(bevk_ctx* c, const uint8_t* const* srcs, int64_t src_stride, in
   CU(cudaEventRecord(c->ev_free[0], c->stream));
   CU(cudaEventRecord(c->ev_free[1], c->stream));
   int half = 0;
+  // Page-locked host frames whose rows are 16-byte friendly are ingested by k_fetch_spans (the SMs read
+  // only the sampled row spans over PCIe); anything else goes through DMA copies.
+  bool zero_copy = !(flags & BEVK_FLAG_BALANCE) && (row % 16 == 0) && (src_stride % 16 == 0) && c->zero_copy_ok;
+  std::vector<const uint8_t*> dev_view((size_t)batch * c->n_cam, nullptr);
+  if (zero_copy) {
+    for (size_t i = 0; i < dev_view.size() && zero_copy; ++i) {
+      cudaPointerAttributes at{};
+      if (!srcs[i] || cudaPointerGetAttributes(&at, srcs[i]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer ||
+          (reinterpret_cast<uintptr_t>(at.devicePointer) & 15)) {
+        zero_copy = false;
+        cudaGetLastError();   // a pageable pointer makes cudaPointerGetAttributes fail on old drivers: not an error here
+      } else {
+        dev_view[i] = static_cast<const uint8_t*>(at.devicePointer);
+      }
+    }
+  }
+  if (zero_copy) {
+    RET(c->d_hptrs.ensure(sizeof(void*) * set_frames * chunk * 2));
+    if (!c->h_hptrs) CU(cudaHostAlloc(reinterpret_cast<void**>(&c->h_hptrs), sizeof(void*) * BEVK_MAX_CAMERAS * 8 * 2, cudaHostAllocDefault));
+  }
+  c->last_h2d_bytes = 0;
   for (int b0 = 0; b0 < batch; b0 += chunk, half ^= 1) {
     const int nb = std::min(chunk, batch - b0);
     uint8_t* dframes = c->d_frames.as<uint8_t>() + (size_t)half * chunk * set_frames * fpad;
     CU(cudaStreamWaitEvent(c->copy_stream, c->ev_free[half], 0));   // this half's previous chunk has been rendered
-    for (int i = 0; i < nb * c->n_cam; ++i) {
+    if (zero_copy) {
+      const uint8_t** hp = c->h_hptrs + (size_t)half * chunk * set_frames;
+      // the pinned pointer staging area of this half was consumed by the copy two chunks ago (ordered by ev_free + stream order)
+      CU(cudaEventSynchronize(c->ev_hp[half]));
+      for (int i = 0; i < nb * c->n_cam; ++i) hp[i] = dev_view[(size_t)b0 * c->n_cam + i];
+      const uint8_t** dhp = c->d_hptrs.as<const uint8_t*>() + (size_t)half * chunk * set_frames;
+      CU(cudaMemcpyAsync(dhp, hp, sizeof(void*) * nb * c->n_cam, cudaMemcpyHostToDevice, c->copy_stream));
+      CU(cudaEventRecord(c->ev_hp[half], c->copy_stream));
+      k_fetch_spans<<<dim3(c->FH, nb * c->n_cam), 128, 0, c->copy_stream>>>(
+          dhp, c->d_ptrs.as<uint8_t*>() + (size_t)half * chunk * set_frames, c->d_spans.as<int2>(), c->n_cam, c->FH,
+          (long long)src_stride, (int)row);
+      LAUNCHED(c);
+      c->last_h2d_bytes += (long long)c->span_fetch_bytes * nb;
+    }
+    for (int i = 0; i < nb * c->n_cam && !zero_copy; ++i) {
       const uint8_t* s = srcs[(size_t)b0 * c->n_cam + i];
       if (!s) return fail(BEVK_ERR_ARG, "null frame pointer %d", b0 * c->n_cam + i);
       uint8_t* d = dframes + (size_t)i * fpad;
       if (flags & BEVK_FLAG_BALANCE) {   // luminance_balance averages V over the whole raw frame: everything goes up
         if ((size_t)src_stride == row) CU(cudaMemcpyAsync(d, s, fbytes, cudaMemcpyHostToDevice, c->copy_stream));
         else CU(cudaMemcpy2DAsync(d, row, s, (size_t)src_stride, row, c->FH, cudaMemcpyHostToDevice, c->copy_stream));
+        c->last_h2d_bytes += (long long)fbytes;
       } else {                           // only the rectangle of the frame this camera's LUT can sample
-        const int* bx = c->cam_box[i % c->n_cam];
-        if (bx[1] > bx[0])
-          CU(cudaMemcpy2DAsync(d + (size_t)bx[0] * row + bx[2], row, s + (size_t)bx[0] * src_stride + bx[2], (size_t)src_stride,
-                               (size_t)(bx[3] - bx[2]), (size_t)(bx[1] - bx[0]), cudaMemcpyHostToDevice, c->copy_stream));
+        for (int bnd = 0; bnd < c->n_bands; ++bnd) {
+          const int* bx = c->cam_box[i % c->n_cam][bnd];
+          if (bx[1] > bx[0]) {
+            CU(cudaMemcpy2DAsync(d + (size_t)bx[0] * row + bx[2], row, s + (size_t)bx[0] * src_stride + bx[2],
+                                 (size_t)src_stride, (size_t)(bx[3] - bx[2]), (size_t)(bx[1] - bx[0]), cudaMemcpyHostToDevice,
+                                 c->copy_stream));
+            c->last_h2d_bytes += (long long)(bx[3] - bx[2]) * (bx[1] - bx[0]);
+          }
+        }
       }
     }
     CU(cudaEventRecord(c->ev_in[half], c->copy_stream));

@@ -251,6 +251,10 @@ class BevEngine:
         L.check(self.ctx.lib.bevk_bev_host_copy_bytes(self.ctx.h, L.FLAG_BALANCE if balance else 0, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def last_h2d_bytes(self) -> int:
+        """Host->device bytes moved by the last run() call."""
+        return int(self.ctx.lib.bevk_bev_last_h2d_bytes(self.ctx.h))
+
     def _conform(self, f: np.ndarray) -> np.ndarray:
         """The reference never validates frame sizes (cv2.remap samples whatever it is given,
         zero outside).  The engine's LUT is compiled for FW x FH, so other sizes are embedded

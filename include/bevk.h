@@ -150,6 +150,9 @@ int bevk_bev_plan_info(bevk_ctx *ctx, int64_t *n_tiles, int64_t *n_items, int64_
  * BALANCE only the rectangle of each frame its camera's LUT can sample is uploaded; with BALANCE
  * the whole frames, because the V means cover them) and device->host (the canvas). */
 int bevk_bev_host_copy_bytes(bevk_ctx *ctx, int flags, int64_t *h2d_per_frame_set, int64_t *d2h_per_frame_set);
+/* Host->device bytes the last bevk_bev_run call actually moved (page-locked frames are ingested span
+ * by span by the SMs, pageable ones by DMA rectangles, BALANCE uploads whole frames). */
+int64_t bevk_bev_last_h2d_bytes(bevk_ctx *ctx);
 /* Items whose source box is staged in shared memory by TMA, and the bytes those boxes
  * move per frame-set (the rest of the items gather straight from global memory). */
 int bevk_bev_stage_info(bevk_ctx *ctx, int64_t *staged_items, int64_t *staged_bytes_per_frame_set);

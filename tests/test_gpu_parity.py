@@ -474,3 +474,30 @@ def test_bev_batch_sizes_and_host_pipeline(ops, fx):
             else:
                 ref = e.run([sets[nb - 1]], car, True)[0]
                 assert (out[nb - 1] == ref).all(), nb
+
+
+def test_bev_pinned_host_frames_zero_copy_ingest(ops, fx):
+    """Page-locked frames take the span-by-span zero-copy ingest (k_fetch_spans) instead of DMA
+    rectangles; results and the reported PCIe bytes must agree with the pageable path / be smaller."""
+    from cameracalibration_b200 import pinned_empty
+    g = fx.geometry(1280, 1024, 1000, 1000)        # pitch 3840 is a multiple of 16
+    e, masks = _engine(ops, fx, g, blend=True, calib=fx.calib)
+    F = fx.frames()
+    sets_pageable = [[np.ascontiguousarray(np.roll(f, 11 * i, axis=0)) for f in F] for i in range(11)]
+    want = e.run(sets_pageable, fx.car())
+    dma_bytes = e.last_h2d_bytes()
+    sets_pinned = []
+    for s in sets_pageable:
+        row = []
+        for f in s:
+            p = pinned_empty(f.shape)
+            p[...] = f
+            row.append(p)
+        sets_pinned.append(row)
+    got = e.run(sets_pinned, fx.car())
+    assert (got == want).all()
+    assert h16(got[0]) == fx.gold["native"]["blend1_balance0"]["car"]
+    assert 0 < e.last_h2d_bytes() < dma_bytes < 11 * 4 * 1280 * 1024 * 3
+    bal = e.run(sets_pinned[:2], fx.car(), balance=True)      # BALANCE needs whole frames: DMA path
+    assert h16(bal[0]) == fx.gold["native"]["blend1_balance1"]["car"]
+    assert e.last_h2d_bytes() == 2 * 4 * 1280 * 1024 * 3
