@@ -377,7 +377,7 @@ def main():
                              "algorithmic_bytes_per_frame_set": {"source_unique_32B_sectors": src_b, "canvas_write": canvas_b}},
                 "clocks": sampler.summary(), "plan": eng.plan_info()}
         if not a.no_cpu_baseline and world == 1:
-            v, cores, sample = cpu_reference(w, calib, masks, n_sets=4, repeats=50, seconds_cap=15.0)
+            v, cores, sample = cpu_reference(w, calib, masks, n_sets=4, repeats=100000, seconds_cap=20.0)
             line["cpu_baseline"] = {"value": v, "unit": unit, "cores": cores, "kind": "port",
                                     "sample": sample + f"; os.cpu_count()={os.cpu_count()}"}
         print(json.dumps(line))
