@@ -17,6 +17,7 @@
 #include "../../include/bevk.h"
 #include "bevk_kernels.cuh"
 #include "bevk_bev.cuh"
+#include "bevk_gather4.cuh"
 
 using namespace bevk;
 
@@ -252,6 +253,13 @@ int bevk_undistort_map(bevk_ctx* c, int model, const double K[9], const double* 
 // ------------------------------------------------------------------ gather dispatch
 template <int MODE>
 static int launch_gather(bevk_ctx* c, const GatherArgs& a, int channels, int interp) {
+  if (channels == 3 && interp == BEVK_INTER_LINEAR && (a.dw % 4) == 0 && a.dpitch == (long long)a.dw * 3 && (a.spitch % 4) == 0 &&
+      a.spitch < (1ll << 31) / std::max(1, a.sh) && (MODE != 0 || a.map2 != nullptr)) {
+    // 4 output pixels per thread, 32-bit tap loads and 12-byte stores
+    k_gather4<MODE><<<dim3((a.dw / 4 + 31) / 32, (a.dh + 7) / 8), 256, 0, c->stream>>>(a);
+    LAUNCHED(c);
+    return BEVK_OK;
+  }
   const dim3 g = grid2d(a.dw, a.dh);
 #define GO(C, L) k_gather<MODE, C, L><<<g, 256, 0, c->stream>>>(a)
   if (interp == BEVK_INTER_LINEAR) {

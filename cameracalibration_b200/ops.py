@@ -39,8 +39,17 @@ def _undistort_map(model, K, D, P, size, ctx):
     return m1, m2
 
 
+def _out(shape, out):
+    """cv2-style optional destination (e.g. a page-locked array from pinned_empty for full-rate D2H)."""
+    if out is None:
+        return np.empty(shape, np.uint8)
+    if out.dtype != np.uint8 or out.shape != tuple(shape) or not out.flags.c_contiguous:
+        raise L.BevkError(f"out must be a C-contiguous uint8 array of shape {tuple(shape)}")
+    return out
+
+
 def remap(src: np.ndarray, map1: np.ndarray, map2: np.ndarray | None, interpolation: int = INTER_LINEAR,
-          ctx: L.Context | None = None) -> np.ndarray:
+          ctx: L.Context | None = None, out: np.ndarray | None = None) -> np.ndarray:
     """cv2.remap with CV_16SC2 (+CV_16UC1) maps, BORDER_CONSTANT 0."""
     ctx = ctx or L.default_context()
     img, sw, sh, ss, ch = L.image_view(src)
@@ -51,18 +60,19 @@ def remap(src: np.ndarray, map1: np.ndarray, map2: np.ndarray | None, interpolat
     m2 = None if map2 is None else np.ascontiguousarray(map2, np.uint16)
     if m2 is not None and m2.shape != (dh, dw):
         raise L.BevkError("map2 must be uint16[h][w] (CV_16UC1)")
-    out = np.empty((dh, dw) if src.ndim == 2 else (dh, dw, ch), np.uint8)
+    out = _out((dh, dw) if src.ndim == 2 else (dh, dw, ch), out)
     L.check(ctx.lib.bevk_remap(ctx.h, L.vptr(img), sw, sh, ss, ch, L.vptr(m1), None if m2 is None else L.vptr(m2),
                                dw, dh, L.vptr(out), dw * ch, _interp(interpolation)))
     return out
 
 
-def warp_perspective(src: np.ndarray, H, dsize, flags: int = INTER_LINEAR, ctx: L.Context | None = None):
+def warp_perspective(src: np.ndarray, H, dsize, flags: int = INTER_LINEAR, ctx: L.Context | None = None,
+                     out: np.ndarray | None = None):
     """cv2.warpPerspective(src, H, dsize, flags) for uint8 images, BORDER_CONSTANT 0."""
     ctx = ctx or L.default_context()
     img, sw, sh, ss, ch = L.image_view(src)
     dw, dh = int(dsize[0]), int(dsize[1])
-    out = np.empty((dh, dw) if src.ndim == 2 else (dh, dw, ch), np.uint8)
+    out = _out((dh, dw) if src.ndim == 2 else (dh, dw, ch), out)
     L.check(ctx.lib.bevk_warp_perspective(ctx.h, L.vptr(img), sw, sh, ss, ch, L.dptr(H), L.vptr(out), dw, dh,
                                           dw * ch, _interp(flags)))
     return out
@@ -143,9 +153,9 @@ class Undistorter:
         L.check(self.ctx.lib.bevk_undistorter_maps(self.ctx.h, self.slot, L.vptr(m1), L.vptr(m2)))
         return m1, m2
 
-    def __call__(self, src: np.ndarray, interpolation: int = INTER_LINEAR) -> np.ndarray:
+    def __call__(self, src: np.ndarray, interpolation: int = INTER_LINEAR, out: np.ndarray | None = None) -> np.ndarray:
         img, sw, sh, ss, ch = L.image_view(src)
-        out = np.empty((self.h, self.w) if src.ndim == 2 else (self.h, self.w, ch), np.uint8)
+        out = _out((self.h, self.w) if src.ndim == 2 else (self.h, self.w, ch), out)
         L.check(self.ctx.lib.bevk_undistort(self.ctx.h, self.slot, L.vptr(img), sw, sh, ss, ch, L.vptr(out),
                                             self.w * ch, _interp(interpolation)))
         return out
