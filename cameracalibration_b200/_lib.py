@@ -52,7 +52,6 @@ SIGNATURES = {
     "bevk_bev_plan_info": (C.c_int, [_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bevk_bev_host_copy_bytes": (C.c_int, [_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bevk_bev_last_h2d_bytes": (C.c_int64, [_p]),
-    "bevk_bev_stage_info": (C.c_int, [_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bevk_launch_count": (C.c_int64, [_p]),
     "bevk_last_kernel_ms": (C.c_int, [_p, C.POINTER(C.c_float)]),
 }

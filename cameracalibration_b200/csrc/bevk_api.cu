@@ -134,7 +134,7 @@ struct bevk_ctx {
   int n_cam = 0, FW = 0, FH = 0, BW = 0, BH = 0;
   BevCam cam[BEVK_MAX_CAMERAS];
   bool planned = false;
-  long long n_tiles = 0, n_items = 0, staged_items = 0, staged_bytes = 0, span_px = 0;
+  long long n_tiles = 0, n_items = 0, span_px = 0;
   int nb_override = 0;   // BEVK_NB tuning override, read at finalize
   int n_bands = 1;
   bool zero_copy_ok = true;                 // BEVK_ZEROCOPY=0 forces the DMA path
@@ -545,7 +545,6 @@ int bevk_bev_finalize(bevk_ctx* c) {
   std::vector<BevItem> items;
   std::vector<uint4> lut;
   tiles.reserve((size_t)tx * ty);
-  c->staged_items = 0; c->staged_bytes = 0;
   c->nb_override = 0;
   if (const char* env = getenv("BEVK_NB")) {   // tuning override of the frame-sets per work unit: 1, 4 or 8
     const int v = atoi(env);
@@ -566,8 +565,6 @@ int bevk_bev_finalize(bevk_ctx* c) {
         const uint8_t* mk = c->cam[k].mask.data();
         bool any = false;
         long long cx = 0, cy = 0;   // source-row changes along canvas x vs canvas y
-        // source bounding box of the in-frame taps of this (tile, camera): rows [by0, by1), bytes [bx0, bx1)
-        int by0 = INT_MAX, by1 = -1, bx0 = INT_MAX, bx1 = -1;
         auto in_frame = [&](int sx, int sy) {
           const long long off = (long long)sy * pitch + (long long)sx * 3;
           return sx >= 0 && sy >= 0 && sx + 1 < FW && sy + 1 < FH && !(pitch & 3u) && off + pitch + 12 <= frame_bytes;
@@ -581,33 +578,11 @@ int bevk_bev_finalize(bevk_ctx* c) {
             touch(k, sx, sy); touch(k, sx + 1, sy); touch(k, sx, sy + 1); touch(k, sx + 1, sy + 1);
             if (x + 1 < BW && mk[p + 1]) cx += std::abs(m1[k][2 * (p + 1) + 1] - sy);
             if (y + 1 < BH && mk[p + BW]) cy += std::abs(m1[k][2 * (p + BW) + 1] - sy);
-            if (in_frame(sx, sy)) {
-              const int wl = (3 * sx) & ~3;   // first word the fast path reads; it may read 12 bytes from there
-              by0 = std::min(by0, sy); by1 = std::max(by1, sy + 2);
-              bx0 = std::min(bx0, wl); bx1 = std::max(bx1, wl + 12);
-            }
           }
         if (!any) continue;
         BevItem item{};
         item.cam = k;
         item.orient = cy < cx ? 1 : 0;
-        // Source-box staging in shared memory is disabled: measured slower than the batched global
-        // gather in round 1 (experiments/).  The box statistics are still
-        // collected for bevk_bev_stage_info; no LUT entry is made box-relative.
-        const bool use_staging = false;
-        if (by1 > by0 && (pitch % 16u) == 0) {
-          int xa = bx0 & ~15, xb = (bx1 + 15) & ~15;
-          if (xb > (int)pitch) { xa -= xb - (int)pitch; xb = (int)pitch; }   // pitch % 16 == 0 keeps xa aligned
-          xa = std::max(xa, 0);
-          const long long bytes = (long long)(by1 - by0) * (xb - xa);
-          if (bytes <= 12288) {
-            item.staged = use_staging ? 1 : 0;
-            item.src_off = (unsigned)((long long)by0 * pitch + xa);
-            item.rows = by1 - by0; item.row_bytes = xb - xa;
-            item.pad0 = by0; item.pad1 = xa;
-            c->staged_items++; c->staged_bytes += bytes;
-          }
-        }
         const size_t base = lut.size();
         lut.resize(base + TILE * TILE, make_uint4(0u, 0u, 0u, 0u));
         for (int kk = 0; kk < 4; ++kk)
@@ -630,8 +605,6 @@ int bevk_bev_finalize(bevk_ctx* c) {
               // per-tap checked path
               e.w |= LUT_BORDER;
               e.x = (unsigned)(unsigned short)sx | ((unsigned)(unsigned short)sy << 16);
-            } else if (item.staged) {
-              e.x = (unsigned)((sy - item.pad0) * item.row_bytes + (3 * sx - item.pad1));
             } else {
               e.x = (unsigned)((long long)sy * pitch + (long long)sx * 3);
             }
@@ -740,14 +713,6 @@ int bevk_bev_host_copy_bytes(bevk_ctx* c, int flags, int64_t* h2d, int64_t* d2h)
   return BEVK_OK;
 }
 
-int bevk_bev_stage_info(bevk_ctx* c, int64_t* staged_items, int64_t* staged_bytes) {
-  RET(use(c));
-  if (!c->planned) return fail(BEVK_ERR_ARG, "bevk_bev_finalize not called");
-  if (staged_items) *staged_items = c->staged_items;
-  if (staged_bytes) *staged_bytes = c->staged_bytes;
-  return BEVK_OK;
-}
-
 // ------------------------------------------------------------------ BEV engine: run
 static int run_device(bevk_ctx* c, const void* d_srcs, int batch, const void* d_car, int flags, void* d_out, int cam_lo,
                       int cam_hi) {
@@ -764,8 +729,6 @@ static int run_device(bevk_ctx* c, const void* d_srcs, int batch, const void* d_
   P.car = reinterpret_cast<const uint8_t*>(d_car);
   P.cam_lo = cam_lo; P.cam_hi = cam_hi;
   P.n_tiles = (int)c->n_tiles; P.batch = batch;
-  P.stage = 1;
-  if (const char* env = getenv("BEVK_STAGE")) P.stage = atoi(env) != 0;   // A/B switch for the TMA source staging
   // frame-sets per work unit: 4 amortises the LUT decode over a batch; 1 for single frames
   int nbu = batch >= 4 ? 4 : 1;
   if (c->nb_override) nbu = c->nb_override;

@@ -38,12 +38,8 @@ constexpr int ACC_WPITCH = TILE + 1;               // 33 words per row: rows and
 constexpr int ACC_WORDS = TILE * ACC_WPITCH;       // 1056 words = 4224 B per frame-set
 constexpr unsigned LUT_ACTIVE = 1u << 28, LUT_BORDER = 2u << 28;
 
-struct BevItem {           // 32 B
+struct BevItem {
   int cam, orient;         // orient 0: lanes along canvas x, 1: lanes along canvas y
-  int staged;              // reserved (shared-memory source staging, see experiments/)
-  unsigned src_off;
-  int rows, row_bytes;
-  int pad0, pad1;
 };
 
 struct BevParams {
@@ -58,7 +54,6 @@ struct BevParams {
   const uint8_t* car;
   unsigned long long* csum;     // [batch * 3] channel sums of the composed canvas (BALANCE)
   int cam_lo, cam_hi;
-  int stage;                    // reserved
 };
 
 __device__ __forceinline__ unsigned ldg32(const uint8_t* p) { return __ldg(reinterpret_cast<const unsigned*>(p)); }

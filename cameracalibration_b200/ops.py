@@ -215,10 +215,7 @@ class BevEngine:
     def plan_info(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         L.check(self.ctx.lib.bevk_bev_plan_info(self.ctx.h, C.byref(a), C.byref(b), C.byref(c)))
-        d, e = C.c_int64(), C.c_int64()
-        L.check(self.ctx.lib.bevk_bev_stage_info(self.ctx.h, C.byref(d), C.byref(e)))
-        return {"tiles": a.value, "items": b.value, "lut_bytes": c.value, "staged_items": d.value,
-                "staged_bytes_per_frame_set": e.value}
+        return {"tiles": a.value, "items": b.value, "lut_bytes": c.value}
 
     def run(self, frame_sets, car: np.ndarray | None = None, balance: bool = False, out: np.ndarray | None = None):
         """frame_sets: list (batch) of lists (n_cam) of uint8[FH][FW][3] arrays.  Returns

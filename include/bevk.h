@@ -153,9 +153,6 @@ int bevk_bev_host_copy_bytes(bevk_ctx *ctx, int flags, int64_t *h2d_per_frame_se
 /* Host->device bytes the last bevk_bev_run call actually moved (page-locked frames are ingested span
  * by span by the SMs, pageable ones by DMA rectangles, BALANCE uploads whole frames). */
 int64_t bevk_bev_last_h2d_bytes(bevk_ctx *ctx);
-/* Items whose source box is staged in shared memory by TMA, and the bytes those boxes
- * move per frame-set (the rest of the items gather straight from global memory). */
-int bevk_bev_stage_info(bevk_ctx *ctx, int64_t *staged_items, int64_t *staged_bytes_per_frame_set);
 /* Kernel launches issued by this ctx since creation (bench "gpu_launches"). */
 int64_t bevk_launch_count(bevk_ctx *ctx);
 /* Milliseconds spent in the last bevk_bev_run_device call's kernels, measured with
