@@ -501,3 +501,27 @@ def test_bev_pinned_host_frames_zero_copy_ingest(ops, fx):
     bal = e.run(sets_pinned[:2], fx.car(), balance=True)      # BALANCE needs whole frames: DMA path
     assert h16(bal[0]) == fx.gold["native"]["blend1_balance1"]["car"]
     assert e.last_h2d_bytes() == 2 * 4 * 1280 * 1024 * 3
+
+
+def test_bev_odd_frame_width_and_strided_frames(ops, fx):
+    """Frame widths whose row pitch is not a multiple of 4 (every LUT entry takes the per-tap checked
+    path, k_vsum its unaligned path) and frames that are strided views of larger host arrays."""
+    g = fx.geometry(333, 250, 203, 177)
+    e, masks = _engine(ops, fx, g, blend=True)
+    ref = C.RefBev(fx.scaled_calib(g), g, True, False, masks=masks)
+    F = fx.frames(g.FW, g.FH)
+    car = fx.car(g.BW, g.BH)
+    for balance in (False, True):
+        ref.balance = balance
+        assert (e.run([F], car, balance)[0] == ref(*F, car)).all(), balance
+    g2 = fx.geometry(640, 480, 300, 300)
+    e2, masks2 = _engine(ops, fx, g2, blend=False)
+    ref2 = C.RefBev(fx.scaled_calib(g2), g2, False, False, masks=masks2)
+    F2 = fx.frames(g2.FW, g2.FH)
+    big = [np.zeros((500, 700, 3), np.uint8) for _ in F2]
+    views = []
+    for b, f in zip(big, F2):
+        b[10:490, 30:670] = f
+        views.append(b[10:490, 30:670])          # row stride 2100 B > 1920 B row
+    assert (e2.run([views])[0] == ref2(*F2)).all()
+    assert (e2.run([views, F2])[1] == ref2(*F2)).all() if views[0].strides[0] == F2[0].strides[0] else True
