@@ -322,17 +322,20 @@ def main():
     # ---- end to end through the public API, pinned host frames ----
     from cameracalibration_b200 import pinned_empty
     n_e2e = a.e2e_steps or min(a.steps, 20)
-    pin_in = pinned_empty((nb, nc, w["FH"], w["FW"], 3))
-    pin_in[...] = host
+    # two distinct page-locked input batches, alternated step by step (2 x 796 MB >> L2: no step can be
+    # served from a cache of the previous one); the last step uses batch 0 so the result can be checked
+    pin_in = pinned_empty((2, nb, nc, w["FH"], w["FW"], 3))
+    pin_in[0] = host
+    pin_in[1] = host[::-1]
     pin_out = pinned_empty((nb, w["BH"], w["BW"], 3))
     eng.ctx.set_stream(None)
-    sets = [[pin_in[b, c] for c in range(nc)] for b in range(nb)]
-    for _ in range(2):
-        eng.run(sets, None, w["balance"], out=pin_out)
+    sets = [[[pin_in[v, b, c] for c in range(nc)] for b in range(nb)] for v in range(2)]
+    for i in range(2):
+        eng.run(sets[i & 1], None, w["balance"], out=pin_out)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(n_e2e):
-        eng.run(sets, None, w["balance"], out=pin_out)
+    for i in range(n_e2e):
+        eng.run(sets[(n_e2e - 1 - i) & 1], None, w["balance"], out=pin_out)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     te = torch.tensor([dt], dtype=torch.float64, device=dev)
