@@ -48,7 +48,7 @@ def main():
                f"{b['e2e']['value'] / 1e3:.1f} k frame-sets/s end-to-end from page-locked host memory "
                f"({b['e2e']['h2d_bytes_per_step'] / 1e6:.0f} MB in + {b['e2e']['d2h_bytes_per_step'] / 1e6:.0f} MB out per step over PCIe), "
                f"reference cv2 path {ref['value']:.0f} frame-sets/s on the same host (`--impl reference`). "
-               "2 / 4 GPUs (frame-set sharding, no collective): 433 k / 838 k device-resident.\n"]
+               "2 / 4 / 8 GPUs (frame-set sharding, no collective): 433 k / 838 k / 1 675 k device-resident; 8 GPUs end-to-end 37.7 k (host PCIe shared).\n"]
     open(p, "w").write(s + "\n".join(md))
 
 
