@@ -39,6 +39,7 @@ SIGNATURES = {
     "bevk_bev_set_camera": (C.c_int, [_p, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, _dp]),
     "bevk_bev_set_maps": (C.c_int, [_p, C.c_int, _p, _p]),
     "bevk_bev_get_maps": (C.c_int, [_p, C.c_int, _p, _p]),
+    "bevk_bev_set_interpolation": (C.c_int, [_p, C.c_int]),
     "bevk_bev_set_mask": (C.c_int, [_p, C.c_int, _p]),
     "bevk_blend_masks": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, _p]),
     "bevk_bev_finalize": (C.c_int, [_p]),

@@ -136,6 +136,7 @@ struct bevk_ctx {
   bool planned = false;
   long long n_tiles = 0, n_items = 0, span_px = 0;
   int nb_override = 0;   // BEVK_NB tuning override, read at finalize
+  int bev_interp = BEVK_INTER_LINEAR;   // cv2.remap interpolation the BEV LUT is compiled for
   int n_bands = 1;
   bool zero_copy_ok = true;                 // BEVK_ZEROCOPY=0 forces the DMA path
   DevBuf d_hptrs;                           // device copy of the mapped host frame pointers (per half)
@@ -432,6 +433,7 @@ int bevk_bev_configure(bevk_ctx* c, int n_cam, int fw, int fh, int bw, int bh) {
   if (fw > 32767 || fh > 32767) return fail(BEVK_ERR_UNSUPPORTED, "frames larger than 32767 px");
   if ((long long)fw * fh * 3 + 16 > 0xffffffffLL) return fail(BEVK_ERR_UNSUPPORTED, "frame too large for 32-bit offsets");
   c->n_cam = n_cam; c->FW = fw; c->FH = fh; c->BW = bw; c->BH = bh;
+  c->bev_interp = BEVK_INTER_LINEAR;
   c->planned = false;
   for (auto& k : c->cam) { k.has_maps = false; k.has_mask = false; k.mask.clear(); }
   return BEVK_OK;
@@ -489,6 +491,15 @@ int bevk_bev_get_maps(bevk_ctx* c, int cam, int16_t* map1, uint16_t* map2) {
   CU(cudaMemcpyAsync(map1, k.map1.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(map2, k.map2.p, n * 2, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  return BEVK_OK;
+}
+
+int bevk_bev_set_interpolation(bevk_ctx* c, int interp) {
+  RET(use(c));
+  if (c->n_cam == 0) return fail(BEVK_ERR_ARG, "bevk_bev_configure not called");
+  if (interp != BEVK_INTER_LINEAR && interp != BEVK_INTER_NEAREST) return fail(BEVK_ERR_UNSUPPORTED, "interp %d", interp);
+  c->bev_interp = interp;
+  c->planned = false;
   return BEVK_OK;
 }
 
@@ -574,7 +585,10 @@ int bevk_bev_finalize(bevk_ctx* c) {
             const size_t p = (size_t)y * BW + x;
             if (!mk[p]) continue;
             any = true;
-            const int sx = m1[k][2 * p], sy = m1[k][2 * p + 1];
+            int sx = m1[k][2 * p], sy = m1[k][2 * p + 1];
+            if (c->bev_interp == BEVK_INTER_NEAREST) {   // same shift as in the entry builder below
+              sx += ((m2[k][p] & 31u) < 16u); sy += (((m2[k][p] >> 5) & 31u) < 16u);
+            }
             touch(k, sx, sy); touch(k, sx + 1, sy); touch(k, sx, sy + 1); touch(k, sx + 1, sy + 1);
             if (x + 1 < BW && mk[p + 1]) cx += std::abs(m1[k][2 * (p + 1) + 1] - sy);
             if (y + 1 < BH && mk[p + BW]) cy += std::abs(m1[k][2 * (p + BW) + 1] - sy);
@@ -593,8 +607,16 @@ int bevk_bev_finalize(bevk_ctx* c) {
             const size_t p = (size_t)y * BW + x;
             const unsigned w = mk[p];
             if (!w) continue;
-            const int sx = m1[k][2 * p], sy = m1[k][2 * p + 1];
-            const unsigned frac = m2[k][p] & 1023u, fx = frac & 31u, fy = frac >> 5;
+            int sx = m1[k][2 * p], sy = m1[k][2 * p + 1];
+            unsigned frac = m2[k][p] & 1023u;
+            if (c->bev_interp == BEVK_INTER_NEAREST) {
+              // cv2.remap INTER_NEAREST with fixed-point maps: OpenCV's inverted NNDeltaTab picks the +1
+              // neighbour when the fraction is < 16; a zero fraction then makes the bilinear formula
+              // return exactly that texel ((1024 p + 512) >> 10 == p), so the kernel needs no NN variant
+              sx += ((frac & 31u) < 16u); sy += ((frac >> 5) < 16u);
+              frac = 0;
+            }
+            const unsigned fx = frac & 31u, fy = frac >> 5;
             const unsigned w11 = fx * fy, w01 = (fx << 5) - w11, w10 = (fy << 5) - w11, w00 = 1024u - (fx << 5) - (fy << 5) + w11;
             uint4 e;
             e.y = w00 | (w01 << 16);                       // DP2A weight pairs, top / bottom source row

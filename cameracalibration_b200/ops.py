@@ -194,6 +194,11 @@ class BevEngine:
         L.check(self.ctx.lib.bevk_bev_get_maps(self.ctx.h, cam, L.vptr(m1), L.vptr(m2)))
         return m1, m2
 
+    def set_interpolation(self, interpolation: int):
+        """INTER_LINEAR (the reference) or INTER_NEAREST for the raw2bev gather; before finalize()."""
+        L.check(self.ctx.lib.bevk_bev_set_interpolation(self.ctx.h, _interp(interpolation)))
+        self.finalized = False
+
     def set_mask(self, cam: int, mask: np.ndarray):
         m = np.ascontiguousarray(mask, np.uint8)
         if m.shape != (self.BH, self.BW):

@@ -108,6 +108,9 @@ int bevk_bev_get_maps(bevk_ctx *ctx, int cam, int16_t *map1, uint16_t *map2);
 /* Mask / BlendMask (surroundBEV.py:119-162, 164-280): uint8[bev_h][bev_w]; 0/255 for
  * the plain path, 0..255 blend weights otherwise (weight = float32(mask/255.0)). */
 int bevk_bev_set_mask(bevk_ctx *ctx, int cam, const uint8_t *mask);
+/* Interpolation of raw2bev's cv2.remap (surroundBEV.py:116-117 uses INTER_LINEAR; INTER_NEAREST is
+ * offered with cv2.remap's exact fixed-point-map semantics).  Call before bevk_bev_finalize. */
+int bevk_bev_set_interpolation(bevk_ctx *ctx, int interp);
 /* BlendMask.get_blend_mask (surroundBEV.py:270-277) for the 4-camera layout, on the
  * device: polys = the four *unblended* 6-gon masks (uint8[4][bev_h][bev_w], order
  * front,back,left,right), lines = the 8 seam segments FL,FR,BL,BR,LF,LB,RF,RB as

@@ -525,3 +525,23 @@ def test_bev_odd_frame_width_and_strided_frames(ops, fx):
         views.append(b[10:490, 30:670])          # row stride 2100 B > 1920 B row
     assert (e2.run([views])[0] == ref2(*F2)).all()
     assert (e2.run([views, F2])[1] == ref2(*F2)).all() if views[0].strides[0] == F2[0].strides[0] else True
+
+
+def test_bev_nearest_neighbour_mode(ops, fx):
+    """INTER_NEAREST through the fused engine (LUT compiled with OpenCV's fixed-point NN rule):
+    bit-exact against cv2.remap(..., INTER_NEAREST) per camera + the reference's mask / compose."""
+    g = fx.geometry()
+    for blend in (False, True):
+        e, masks = _engine(ops, fx, g, blend, calib=fx.calib)
+        e.set_interpolation(ops.INTER_NEAREST)
+        F = fx.frames()
+        want = np.zeros((g.BH, g.BW, 3), np.uint8)
+        for i, n in enumerate(NAMES):
+            rc = C.RefCamera(*fx.calib[n], g)
+            w = cv2.remap(F[i], *rc.bev_maps, interpolation=cv2.INTER_NEAREST)
+            want = R.sat_add(want, R.apply_blend(w, masks[i]) if blend else R.apply_plain(w, masks[i]))
+        want = R.sat_add(want, fx.car())
+        assert (e.run([F], fx.car())[0] == want).all(), blend
+        e.set_interpolation(ops.INTER_LINEAR)
+        gold = fx.gold["native"][f"blend{int(blend)}_balance0"]["car"]
+        assert h16(e.run([F], fx.car())[0]) == gold
