@@ -15,7 +15,8 @@ Differences from the reference that are deliberate:
   * K/D/H are read from ``args.DATA_DIR`` (default ``<this dir>/data``, the reference's
     layout ``{name}/camera_{name}_{K,D,H}.npy``) or passed as ``calib={name: (K, D, H)}``.
   * ``BevGenerator.run_batch`` renders many frame-sets per call (the reference has no
-    batch API).
+    batch API); ``BevGenerator(..., interpolation=cv2.INTER_NEAREST)`` selects nearest-neighbour
+    sampling with cv2.remap's exact fixed-point-map semantics (the reference always uses bilinear).
 """
 from __future__ import annotations
 
@@ -269,7 +270,7 @@ class BlendMask:
 
 # ----------------------------------------------------------------------------------------
 class BevGenerator:
-    def __init__(self, blend=None, balance=None, calib=None):
+    def __init__(self, blend=None, balance=None, calib=None, interpolation=None):
         self.init_args()
         g = self._g = _Geo()
         self.blend = args.BLEND_FLAG if blend is None else blend
@@ -277,6 +278,8 @@ class BevGenerator:
         self.cameras = [Camera(n, None if calib is None else calib[n], g) for n in NAMES]
         self.masks = [(BlendMask if self.blend else Mask)(n, g) for n in NAMES]
         self.engine = ops.BevEngine(len(NAMES), (g.FW, g.FH), (g.BW, g.BH))
+        if interpolation is not None:   # extension: cv2.INTER_NEAREST (0) / cv2.INTER_LINEAR (1, the reference)
+            self.engine.set_interpolation(interpolation)
         for i, (cam, mk) in enumerate(zip(self.cameras, self.masks)):
             self.engine.set_camera(i, cam.camera_mat, cam.dist_coeff, cam.camera_mat_dst, g.und_size, cam.homography)
             self.engine.set_mask(i, mk.mask)
