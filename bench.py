@@ -235,6 +235,17 @@ def main():
         ref = C.RefBev(calib, g, w["blend"], w["balance"], masks=masks)
         per_step = 4   # bounded sample: 4 of the 32 frame-sets per step
         sets = synthetic_frames(w["FW"], w["FH"], w["n_cam"], per_step, seed=7)
+        if not os.environ.get("BEVK_REF_THREADS"):
+            # give the reference every host thread it can use: probe cv2's default pool and all cores, keep the faster
+            probes = {}
+            for th in sorted({cv2.getNumThreads(), os.cpu_count() or 1}):
+                cv2.setNumThreads(th)
+                ref(*sets[0])
+                t0 = time.perf_counter()
+                for s_ in sets[:2]:
+                    ref(*s_)
+                probes[th] = time.perf_counter() - t0
+            cv2.setNumThreads(min(probes, key=probes.get))
         for _ in range(max(1, a.warmup)):
             ref(*sets[0])
         t0 = time.perf_counter()
