@@ -1,11 +1,7 @@
-"""Surround Camera Bird Eye View Generator on the B200 engine.
+"""Bird's-eye-view stitching of four fisheye cameras on the B200 engine (libbevk.so).
 
-    from cameracalibration_b200.SurroundBirdEyeView import BevGenerator
-    bev = BevGenerator()                       # real-time path
-    surround = bev(front, back, left, right)
-    bev = BevGenerator(blend=True, balance=True)
-    surround = bev(front, back, left, right, car)
-
-    args = BevGenerator.get_args(); args.CAR_WIDTH = 200; args.CAR_HEIGHT = 350
+``BevGenerator`` keeps the reference's constructor and call signature; geometry comes from the
+namespace returned by ``BevGenerator.get_args()`` and is read when a generator is constructed.
+See surroundBEV.py in this package for the differences that are deliberate.
 """
 from .surroundBEV import BevGenerator  # noqa: F401

@@ -1,8 +1,12 @@
-"""Batch fisheye undistortion (the reference's Tools/undistort.py:25-77) on the GPU: the
-map is built once on the device and stays there; every image is one H2D copy, one
-gather kernel and one D2H copy.  File decode / encode stays on the host with cv2, as in
-the reference.  Same command-line flags; ``-load`` additionally accepts 0/1/true/false
-(the reference's ``type=bool`` makes every non-empty string True)."""
+"""Batch fisheye undistortion on the GPU -- counterpart of the reference's Tools/undistort.py:25-77.
+
+The undistortion map is built once on the device and never leaves it; each image then costs one
+upload, one gather kernel and one download.  Decoding / encoding image files stays on the host with
+cv2, as in the reference.  The command line accepts the reference's flags with the same defaults;
+boolean flags additionally understand 0/1/true/false (the reference's ``type=bool`` turns every
+non-empty string into True), and ``-fused 1`` evaluates the camera model inside the gather kernel
+instead of keeping a map in HBM.
+"""
 from __future__ import annotations
 
 import argparse
@@ -12,78 +16,85 @@ import numpy as np
 
 from .. import ops
 
+# intrinsics of the reference's sample camera (Tools/undistort.py:28-32), used when -load is off
+_SAMPLE_K = (350.4931893001142, 0.0, 647.6297467576265,
+             0.0, 352.43072872484805, 513.5196785119657,
+             0.0, 0.0, 1.0)
+_SAMPLE_D = (-0.03367245449576437, 0.015380779195912842, -0.018654590946883556, 0.0058128945633924185)
 
-def _flag(s):
-    return str(s).lower() not in ("0", "false", "no", "")
-
-
-def make_parser():
-    p = argparse.ArgumentParser(description="Fisheye Camera Undistortion (B200)")
-    p.add_argument("-width", default=1280, type=int)
-    p.add_argument("-height", default=1024, type=int)
-    p.add_argument("-load", default=True, type=_flag)
-    p.add_argument("-path_read", default="./data/", type=str)
-    p.add_argument("-path_save", default="./", type=str)
-    p.add_argument("-path_k", default="./data/camera_0_K.npy", type=str)
-    p.add_argument("-path_d", default="./data/camera_0_D.npy", type=str)
-    p.add_argument("-focalscale", default=1, type=float)
-    p.add_argument("-sizescale", default=1, type=float)
-    p.add_argument("-offset_h", default=0, type=float)
-    p.add_argument("-offset_v", default=0, type=float)
-    p.add_argument("-srcformat", default="jpg", type=str)
-    p.add_argument("-dstformat", default="jpg", type=str)
-    p.add_argument("-quality", default=100, type=int)
-    p.add_argument("-name", default=None, type=str)
-    p.add_argument("-fused", default=False, type=_flag, help="evaluate the camera model in-kernel (no map in HBM)")
-    return p
+_FLAGS = (  # name, default, converter
+    ("width", 1280, int), ("height", 1024, int), ("load", True, "flag"),
+    ("path_read", "./data/", str), ("path_save", "./", str),
+    ("path_k", "./data/camera_0_K.npy", str), ("path_d", "./data/camera_0_D.npy", str),
+    ("focalscale", 1, float), ("sizescale", 1, float), ("offset_h", 0, float), ("offset_v", 0, float),
+    ("srcformat", "jpg", str), ("dstformat", "jpg", str), ("quality", 100, int), ("name", None, str),
+    ("fused", False, "flag"),
+)
 
 
-DEFAULT_K = [[350.4931893001142, 0.0, 647.6297467576265], [0.0, 352.43072872484805, 513.5196785119657], [0.0, 0.0, 1.0]]
-DEFAULT_D = [[-0.03367245449576437], [0.015380779195912842], [-0.018654590946883556], [0.0058128945633924185]]
+def _as_flag(text) -> bool:
+    return str(text).strip().lower() not in ("", "0", "false", "no", "off")
 
 
-def build_undistorter(a) -> ops.Undistorter:
-    if not a.load:
-        K, D = np.array(DEFAULT_K), np.array(DEFAULT_D)
-    else:
-        if not os.path.exists(a.path_k):
-            raise Exception("Camera K File Path not exist")
-        if not os.path.exists(a.path_d):
-            raise Exception("Camera D File Path not exist")
-        K, D = np.load(a.path_k), np.load(a.path_d)
-    P = K.copy()
-    P[0, 0] *= a.focalscale
-    P[1, 1] *= a.focalscale
-    P[0, 2] = a.width / 2 * a.sizescale + a.offset_h
-    P[1, 2] = a.height / 2 * a.sizescale + a.offset_v
-    return ops.Undistorter(K, D, P, (int(a.width * a.sizescale), int(a.height * a.sizescale)), fused=a.fused)
+def make_parser() -> argparse.ArgumentParser:
+    parser = argparse.ArgumentParser(description="Fisheye camera undistortion of a directory of images (B200)")
+    for name, default, conv in _FLAGS:
+        parser.add_argument("-" + name, default=default, type=_as_flag if conv == "flag" else conv)
+    return parser
+
+
+def _intrinsics(opts):
+    if not opts.load:
+        return np.array(_SAMPLE_K).reshape(3, 3), np.array(_SAMPLE_D).reshape(4, 1)
+    for path, what in ((opts.path_k, "K"), (opts.path_d, "D")):
+        if not os.path.exists(path):
+            raise Exception(f"Camera {what} File Path not exist")
+    return np.load(opts.path_k), np.load(opts.path_d)
+
+
+def build_undistorter(opts) -> ops.Undistorter:
+    """Destination intrinsics as the reference forms them (:42-46): scaled focal length, optical axis
+    centred on the scaled frame plus the optional offsets."""
+    K, D = _intrinsics(opts)
+    P = np.array(K, np.float64)
+    P[0, 0] *= opts.focalscale
+    P[1, 1] *= opts.focalscale
+    P[0, 2] = opts.width / 2 * opts.sizescale + opts.offset_h
+    P[1, 2] = opts.height / 2 * opts.sizescale + opts.offset_v
+    size = (int(opts.width * opts.sizescale), int(opts.height * opts.sizescale))
+    return ops.Undistorter(K, D, P, size, fused=opts.fused)
+
+
+def _save(cv2, opts, stem_in_save_dir, bare_stem, img):
+    if opts.dstformat == "jpg":
+        cv2.imwrite(stem_in_save_dir + ".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, opts.quality])
+    elif opts.dstformat == "png":
+        cv2.imwrite(stem_in_save_dir + ".png", img, [cv2.IMWRITE_PNG_COMPRESSION, opts.quality])
+    else:   # the reference writes other formats next to the working directory
+        cv2.imwrite(bare_stem + "." + opts.dstformat, img)
 
 
 def main(argv=None):
     import cv2
-    a = make_parser().parse_args(argv)
-    und = build_undistorter(a)
-    if not os.path.exists(a.path_read):
-        raise Exception("Original Image Read Path not exist")
-    if not os.path.exists(a.path_save):
-        raise Exception("Undistortion Image Save Path not exist")
-    index, done = 1, []
-    for filename in os.listdir(a.path_read):
-        if filename[-4:] != "." + a.srcformat:
+    opts = make_parser().parse_args(argv)
+    undistorter = build_undistorter(opts)
+    for path, message in ((opts.path_read, "Original Image Read Path not exist"),
+                          (opts.path_save, "Undistortion Image Save Path not exist")):
+        if not os.path.exists(path):
+            raise Exception(message)
+    suffix = "." + opts.srcformat
+    written, counter = [], 1
+    for entry in os.listdir(opts.path_read):
+        if entry[-4:] != suffix:
             continue
-        img = und(cv2.imread(os.path.join(a.path_read, filename)))
-        if a.name is not None:
-            filename = a.name + "_{:04d}.".format(index) + a.srcformat
-            index += 1
-        stem = os.path.join(a.path_save, filename[:-4])
-        if a.dstformat == "jpg":
-            cv2.imwrite(stem + ".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, a.quality])
-        elif a.dstformat == "png":
-            cv2.imwrite(stem + ".png", img, [cv2.IMWRITE_PNG_COMPRESSION, a.quality])
-        else:
-            cv2.imwrite(filename[:-4] + "." + a.dstformat, img)
-        done.append(filename)
-    return done
+        result = undistorter(cv2.imread(os.path.join(opts.path_read, entry)))
+        if opts.name is not None:
+            entry = "{}_{:04d}.{}".format(opts.name, counter, opts.srcformat)
+            counter += 1
+        stem = entry[:-4]
+        _save(cv2, opts, os.path.join(opts.path_save, stem), stem, result)
+        written.append(entry)
+    return written
 
 
 if __name__ == "__main__":
