@@ -5,7 +5,8 @@ upload, one gather kernel and one download.  Decoding / encoding image files sta
 cv2, as in the reference.  The command line accepts the reference's flags with the same defaults;
 boolean flags additionally understand 0/1/true/false (the reference's ``type=bool`` turns every
 non-empty string into True), and ``-fused 1`` evaluates the camera model inside the gather kernel
-instead of keeping a map in HBM.
+instead of keeping a map in HBM; ``-workers N`` sizes the decode/encode thread pool that overlaps
+the image files' JPEG/PNG work with the GPU calls.
 """
 from __future__ import annotations
 
@@ -28,7 +29,7 @@ _FLAGS = (  # name, default, converter
     ("path_k", "./data/camera_0_K.npy", str), ("path_d", "./data/camera_0_D.npy", str),
     ("focalscale", 1, float), ("sizescale", 1, float), ("offset_h", 0, float), ("offset_v", 0, float),
     ("srcformat", "jpg", str), ("dstformat", "jpg", str), ("quality", 100, int), ("name", None, str),
-    ("fused", False, "flag"),
+    ("fused", False, "flag"), ("workers", min(8, os.cpu_count() or 1), int),
 )
 
 
@@ -74,6 +75,47 @@ def _save(cv2, opts, stem_in_save_dir, bare_stem, img):
         cv2.imwrite(bare_stem + "." + opts.dstformat, img)
 
 
+def run_directory(opts, undistorter, cv2):
+    """Decode -> undistort -> encode over a directory, overlapped: a thread pool decodes the next files
+    and encodes finished ones (cv2 releases the GIL in imread/imwrite) while the GPU call for the current
+    image runs on the calling thread.  Files are processed and numbered in ``os.listdir`` order exactly as
+    the reference's serial loop does (:59-77); at most ``2 * workers`` decoded images are held at a time."""
+    from collections import deque
+    from concurrent.futures import ThreadPoolExecutor
+
+    suffix = "." + opts.srcformat
+    entries = [e for e in os.listdir(opts.path_read) if e[-4:] == suffix]
+    workers = max(1, int(opts.workers))
+    written, encodes = [], deque()
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        decodes, upcoming = deque(), iter(entries)
+
+        def top_up():
+            while len(decodes) < 2 * workers:
+                entry = next(upcoming, None)
+                if entry is None:
+                    return
+                decodes.append((entry, pool.submit(cv2.imread, os.path.join(opts.path_read, entry))))
+
+        top_up()
+        counter = 1
+        while decodes:
+            entry, pending = decodes.popleft()
+            top_up()
+            result = undistorter(pending.result())
+            if opts.name is not None:
+                entry = "{}_{:04d}.{}".format(opts.name, counter, opts.srcformat)
+                counter += 1
+            stem = entry[:-4]
+            encodes.append(pool.submit(_save, cv2, opts, os.path.join(opts.path_save, stem), stem, result))
+            while len(encodes) > 2 * workers:
+                encodes.popleft().result()
+            written.append(entry)
+        for job in encodes:
+            job.result()      # surfaces an encoder exception, as the serial loop would
+    return written
+
+
 def main(argv=None):
     import cv2
     opts = make_parser().parse_args(argv)
@@ -82,19 +124,7 @@ def main(argv=None):
                           (opts.path_save, "Undistortion Image Save Path not exist")):
         if not os.path.exists(path):
             raise Exception(message)
-    suffix = "." + opts.srcformat
-    written, counter = [], 1
-    for entry in os.listdir(opts.path_read):
-        if entry[-4:] != suffix:
-            continue
-        result = undistorter(cv2.imread(os.path.join(opts.path_read, entry)))
-        if opts.name is not None:
-            entry = "{}_{:04d}.{}".format(opts.name, counter, opts.srcformat)
-            counter += 1
-        stem = entry[:-4]
-        _save(cv2, opts, os.path.join(opts.path_save, stem), stem, result)
-        written.append(entry)
-    return written
+    return run_directory(opts, undistorter, cv2)
 
 
 if __name__ == "__main__":

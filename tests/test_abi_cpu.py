@@ -97,3 +97,39 @@ def test_docs_name_only_real_entry_points():
         txt = open(os.path.join(ROOT, doc)).read()
         for name in set(re.findall(r"\b(bevk_[a-z0-9_]*[a-z0-9])\b", txt)) - not_functions:
             assert name in declared, f"{doc} mentions {name}, which include/bevk.h does not declare"
+
+
+def test_tools_undistort_directory_pipeline(tmp_path):
+    """Host logic of the overlapped Tools/undistort pipeline (reference Tools/undistort.py:59-77): listing order,
+    -name numbering, format dispatch -- with a stand-in for the GPU call (no device here)."""
+    import cv2
+    import numpy as np
+    from cameracalibration_b200.Tools import undistort as T
+    src, dst = tmp_path / "in", tmp_path / "out"
+    src.mkdir(); dst.mkdir()
+    rng = np.random.default_rng(5)
+    imgs = {f"f{i:02d}.png": rng.integers(0, 256, (24, 32, 3), dtype=np.uint8) for i in range(11)}
+    for n, im in imgs.items():
+        cv2.imwrite(str(src / n), im)
+    (src / "skip.jpg").write_bytes(b"not read")
+    listing = [e for e in os.listdir(src) if e.endswith(".png")]
+    seen = []
+    def fake(img):
+        seen.append(img.copy())
+        return 255 - img
+    for workers in (1, 3):
+        seen.clear()
+        opts = T.make_parser().parse_args(["-path_read", str(src) + "/", "-path_save", str(dst) + "/", "-srcformat", "png",
+                                           "-dstformat", "png", "-quality", "1", "-workers", str(workers)])
+        assert T.run_directory(opts, fake, cv2) == listing
+        assert all((a == imgs[n]).all() for a, n in zip(seen, listing))          # GPU calls happen in listing order
+        for n in listing:
+            assert (cv2.imread(str(dst / n)) == 255 - imgs[n]).all()
+    opts = T.make_parser().parse_args(["-path_read", str(src) + "/", "-path_save", str(dst) + "/", "-srcformat", "png",
+                                       "-dstformat", "png", "-quality", "1", "-name", "cam", "-workers", "2"])
+    assert T.run_directory(opts, fake, cv2) == [f"cam_{i:04d}.png" for i in range(1, 12)]
+    assert (cv2.imread(str(dst / "cam_0003.png")) == 255 - imgs[listing[2]]).all()
+    def boom(img):
+        raise RuntimeError("device lost")
+    with pytest.raises(RuntimeError, match="device lost"):
+        T.run_directory(opts, boom, cv2)
