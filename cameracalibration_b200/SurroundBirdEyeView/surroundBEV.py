@@ -302,6 +302,11 @@ class BevGenerator:
         """frame_sets: iterable of (front, back, left, right) tuples -> uint8[n][BH][BW][3]."""
         return self.engine.run([list(fs) for fs in frame_sets], car, self.balance, out)
 
+    def run_cuda(self, frames, car=None, out=None, stream=None):
+        """Frame-sets that are already on the GPU (uint8 CUDA array [n][4][FH][FW][3] in front/back/left/right
+        order, or nested lists of per-frame CUDA arrays) -> CUDA array [n][BH][BW][3]; nothing crosses PCIe."""
+        return self.engine.run_cuda(frames, car, self.balance, out, stream)
+
 
 FRAME_WIDTH, FRAME_HEIGHT, BEV_WIDTH, BEV_HEIGHT = _geo.FW, _geo.FH, _geo.BW, _geo.BH
 CAR_WIDTH, CAR_HEIGHT, FOCAL_SCALE, SIZE_SCALE = _geo.CW, _geo.CH, _geo.FS, _geo.SS

@@ -45,6 +45,7 @@ SIGNATURES = {
     "bevk_bev_finalize": (C.c_int, [_p]),
     "bevk_bev_run": (C.c_int, [_p, C.POINTER(_p), C.c_int64, C.c_int, _p, C.c_int, _p]),
     "bevk_bev_run_device": (C.c_int, [_p, _p, C.c_int, _p, C.c_int, _p]),
+    "bevk_bev_run_frames": (C.c_int, [_p, _p, C.c_int, _p, C.c_int, _p]),
     "bevk_bev_run_device_cams": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _p]),
     "bevk_sat_sum_device": (C.c_int, [_p, C.POINTER(_p), C.c_int, C.c_uint64, _p, _p]),
     "bevk_apply_mask": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, _p]),

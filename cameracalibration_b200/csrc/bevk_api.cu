@@ -150,6 +150,8 @@ struct bevk_ctx {
   DevBuf d_frames, d_ptrs, d_canvas, d_car, d_vsum, d_delta, d_csum;
   DevBuf d_spans, d_bal, d_bal_ptrs;        // BALANCE: sampled row spans per camera, balanced frame copies + their table
   const void* bal_ptrs_for = nullptr; long long bal_ptrs_n = 0;
+  DevBuf d_user_ptrs;                       // bevk_bev_run_frames: device copy of the caller's frame table
+  std::vector<const void*> user_tab;        // ... and what it currently holds
 };
 
 static int use(bevk_ctx* c) {
@@ -213,7 +215,12 @@ int bevk_ctx_destroy(bevk_ctx* c) {
 
 int bevk_ctx_set_stream(bevk_ctx* c, void* s) {
   RET(use(c));
-  c->stream = s ? reinterpret_cast<cudaStream_t>(s) : c->own;
+  cudaStream_t next = s ? reinterpret_cast<cudaStream_t>(s) : c->own;
+  if (next != c->stream && !c->user_tab.empty()) {   // the cached frame table of bevk_bev_run_frames is ordered on the old stream
+    CU(cudaStreamSynchronize(c->stream));
+    c->user_tab.clear();
+  }
+  c->stream = next;
   return BEVK_OK;
 }
 
@@ -812,6 +819,24 @@ int bevk_bev_run_device(bevk_ctx* c, const void* d_srcs, int batch, const void* 
   RET(use(c));
   c->timed = true;
   return run_device(c, d_srcs, batch, d_car, flags, d_out, 0, BEVK_MAX_CAMERAS);
+}
+
+int bevk_bev_run_frames(bevk_ctx* c, const void* const* frames, int batch, const void* d_car, int flags, void* d_out) {
+  RET(use(c));
+  if (!c->planned) return fail(BEVK_ERR_ARG, "bevk_bev_finalize not called");
+  if (!frames || !d_out) return fail(BEVK_ERR_ARG, "null pointer");
+  if (batch < 1) return fail(BEVK_ERR_ARG, "batch must be >= 1");
+  const size_t n = (size_t)batch * c->n_cam;
+  for (size_t i = 0; i < n; ++i)
+    if (!frames[i] || (reinterpret_cast<uintptr_t>(frames[i]) & 3)) return fail(BEVK_ERR_ARG, "frame %zu null or not 4-byte aligned", i);
+  if (c->user_tab.size() != n || memcmp(c->user_tab.data(), frames, n * sizeof(void*)) != 0) {
+    RET(c->d_user_ptrs.ensure(n * sizeof(void*)));
+    c->user_tab.assign(frames, frames + n);
+    // pageable source: the driver stages it before returning, and stream order protects launches still reading the old table
+    CU(cudaMemcpyAsync(c->d_user_ptrs.p, c->user_tab.data(), n * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+  }
+  c->timed = true;
+  return run_device(c, c->d_user_ptrs.p, batch, d_car, flags, d_out, 0, BEVK_MAX_CAMERAS);
 }
 
 int bevk_bev_run_device_cams(bevk_ctx* c, const void* d_srcs, int batch, int cam_lo, int cam_hi, void* d_out) {

@@ -48,6 +48,30 @@ def _out(shape, out):
     return out
 
 
+def _cuda_ptr(arr, shape):
+    """(device pointer, shape) of a uint8 C-contiguous array exposing ``__cuda_array_interface__``."""
+    iface = getattr(arr, "__cuda_array_interface__", None)
+    if iface is None:
+        raise L.BevkError("expected a CUDA array (an object with __cuda_array_interface__)")
+    got = tuple(iface["shape"])
+    if iface["typestr"] not in ("|u1", "<u1", "=u1"):
+        raise L.BevkError(f"CUDA array must be uint8, got typestr {iface['typestr']}")
+    if shape is not None and got != tuple(shape):
+        raise L.BevkError(f"CUDA array must have shape {tuple(shape)}, got {got}")
+    strides = iface.get("strides")
+    if strides is not None:
+        dense, step = [], 1
+        for n in reversed(got):
+            dense.append(step)
+            step *= n
+        if any(n > 1 and s != d for n, s, d in zip(got, strides, reversed(dense))):
+            raise L.BevkError("CUDA array must be C-contiguous")
+    ptr = iface["data"][0]
+    if not ptr:
+        raise L.BevkError("CUDA array has a null data pointer")
+    return int(ptr), got
+
+
 def remap(src: np.ndarray, map1: np.ndarray, map2: np.ndarray | None, interpolation: int = INTER_LINEAR,
           ctx: L.Context | None = None, out: np.ndarray | None = None) -> np.ndarray:
     """cv2.remap with CV_16SC2 (+CV_16UC1) maps, BORDER_CONSTANT 0."""
@@ -286,6 +310,43 @@ class BevEngine:
             self.finalize()
         L.check(self.ctx.lib.bevk_bev_run_device(self.ctx.h, C.c_void_p(d_srcs_ptr), batch, C.c_void_p(d_car_ptr or None),
                                                  L.FLAG_BALANCE if balance else 0, C.c_void_p(d_out_ptr)))
+
+    def run_cuda(self, frames, car=None, balance: bool = False, out=None, stream: int | None = None):
+        """Frames that already live on the GPU (decoder output, torch / CuPy arrays): no PCIe in the call.
+
+        frames: one uint8 CUDA array [batch][n_cam][FH][FW][3], or a list (batch) of lists (n_cam) of uint8
+        CUDA arrays [FH][FW][3] -- anything exposing ``__cuda_array_interface__``, C-contiguous, on this
+        engine's device.  car / out likewise ([BH][BW][3] / [batch][BH][BW][3]); without ``out`` a torch
+        tensor is allocated.  ``stream``: raw CUDA stream handle the work is enqueued on (default: the ctx
+        stream); the call does not synchronise.  Returns ``out``."""
+        if not self.finalized:
+            self.finalize()
+        frame_shape = (self.FH, self.FW, 3)
+        if hasattr(frames, "__cuda_array_interface__"):
+            base, shape = _cuda_ptr(frames, None)
+            if len(shape) != 5 or tuple(shape[1:]) != (self.n_cam,) + frame_shape:
+                raise L.BevkError(f"frames must be uint8[batch][{self.n_cam}][{self.FH}][{self.FW}][3], got {tuple(shape)}")
+            batch, fb = shape[0], self.FH * self.FW * 3
+            ptrs = [base + i * fb for i in range(batch * self.n_cam)]
+        else:
+            batch, ptrs = len(frames), []
+            for b, fs in enumerate(frames):
+                if len(fs) != self.n_cam:
+                    raise L.BevkError(f"frame-set {b} has {len(fs)} frames, expected {self.n_cam}")
+                ptrs += [_cuda_ptr(f, frame_shape)[0] for f in fs]
+        if batch < 1:
+            raise L.BevkError("batch must be >= 1")
+        if out is None:
+            import torch
+            out = torch.empty((batch, self.BH, self.BW, 3), dtype=torch.uint8, device=torch.device("cuda", self.ctx.device))
+        d_out = _cuda_ptr(out, (batch, self.BH, self.BW, 3))[0]
+        d_car = _cuda_ptr(car, (self.BH, self.BW, 3))[0] if car is not None else None
+        if stream is not None:
+            self.ctx.set_stream(stream)
+        table = (C.c_void_p * len(ptrs))(*ptrs)
+        L.check(self.ctx.lib.bevk_bev_run_frames(self.ctx.h, table, batch, C.c_void_p(d_car), L.FLAG_BALANCE if balance else 0,
+                                                 C.c_void_p(d_out)))
+        return out
 
     def run_device_cams(self, d_srcs_ptr: int, batch: int, cam_lo: int, cam_hi: int, d_out_ptr: int):
         if not self.finalized:

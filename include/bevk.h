@@ -130,6 +130,12 @@ int bevk_bev_run(bevk_ctx *ctx, const uint8_t *const *srcs, int64_t src_stride, 
  * (dense frames, row stride frame_w*3); d_car NULL or device; d_out device.  Only
  * enqueues on the ctx stream.                                                    */
 int bevk_bev_run_device(bevk_ctx *ctx, const void *d_srcs, int batch, const void *d_car, int flags, void *d_out);
+/* Same with the table on the HOST: frames[batch*n_cam] are DEVICE pointers to dense frames (e.g. the
+ * data pointers of torch / CuPy / NVDEC buffers; 4-byte aligned).  The library keeps the device copy of
+ * the table and re-uploads it only when its contents change, so streaming into fixed buffers costs no
+ * copy per call.  Replaces the host frames of BevGenerator.__call__ (surroundBEV.py:312-325) when the
+ * decoder already left them on the GPU.  Only enqueues on the ctx stream.             */
+int bevk_bev_run_frames(bevk_ctx *ctx, const void *const *frames, int batch, const void *d_car, int flags, void *d_out);
 /* Per-camera partial canvases for camera-sharded multi-GPU runs: rank r renders only
  * cameras [cam_lo, cam_hi) into d_out (zero elsewhere); the saturating sum of the
  * ranks' partials equals the full canvas (balance is not supported in this mode). */

@@ -133,3 +133,23 @@ def test_tools_undistort_directory_pipeline(tmp_path):
         raise RuntimeError("device lost")
     with pytest.raises(RuntimeError, match="device lost"):
         T.run_directory(opts, boom, cv2)
+
+
+def test_cuda_array_interface_validation():
+    """Host-side checks of run_cuda's inputs (no device needed: a stand-in object carries the interface)."""
+    from cameracalibration_b200 import _lib as L
+    from cameracalibration_b200 import ops
+
+    class Arr:
+        def __init__(self, shape, strides=None, typestr="|u1", ptr=4096):
+            self.__cuda_array_interface__ = dict(shape=shape, typestr=typestr, data=(ptr, False), strides=strides, version=3)
+
+    assert ops._cuda_ptr(Arr((2, 3, 4)), (2, 3, 4)) == (4096, (2, 3, 4))
+    assert ops._cuda_ptr(Arr((2, 3, 4), (12, 4, 1)), None) == (4096, (2, 3, 4))
+    assert ops._cuda_ptr(Arr((1, 3, 4), (999, 4, 1)), None)[0] == 4096          # stride of a length-1 axis is free
+    for bad, msg in ((Arr((2, 3, 4), (24, 4, 1)), "C-contiguous"), (Arr((2, 3, 4), typestr="<f4"), "uint8"),
+                     (Arr((2, 3, 4), ptr=0), "null"), (object(), "__cuda_array_interface__")):
+        with pytest.raises(L.BevkError, match=msg):
+            ops._cuda_ptr(bad, None)
+    with pytest.raises(L.BevkError, match="shape"):
+        ops._cuda_ptr(Arr((2, 3, 4)), (2, 3, 5))

@@ -545,3 +545,54 @@ def test_bev_nearest_neighbour_mode(ops, fx):
         e.set_interpolation(ops.INTER_LINEAR)
         gold = fx.gold["native"][f"blend{int(blend)}_balance0"]["car"]
         assert h16(e.run([F], fx.car())[0]) == gold
+
+
+def test_bev_frames_already_on_the_gpu(ops, fx):
+    """frame-sets that already live in HBM (torch tensors here, any __cuda_array_interface__
+    object in general) go through bevk_bev_run_frames: same bytes as the host path, table re-uploaded only
+    when it changes, wrong shapes / layouts rejected."""
+    import torch
+    from cameracalibration_b200 import _lib as L
+    g = fx.geometry(1280, 1024, 1000, 1000)
+    e, masks = _engine(ops, fx, g, blend=True, calib=fx.calib)
+    F = fx.frames()
+    host_sets = [[np.ascontiguousarray(np.roll(f, 7 * i, axis=1)) for f in F] for i in range(5)]
+    want = e.run(host_sets, fx.car())
+    want_bal = e.run(host_sets, fx.car(), balance=True)
+    dev = torch.device("cuda", e.ctx.device)
+    stream = torch.cuda.Stream(device=dev)
+    d_all = torch.from_numpy(np.stack([np.stack(s) for s in host_sets])).to(dev)          # [5][4][FH][FW][3]
+    d_car = torch.from_numpy(fx.car()).to(dev)
+    torch.cuda.synchronize()
+    out = e.run_cuda(d_all, d_car, stream=stream.cuda_stream)
+    stream.synchronize()
+    assert isinstance(out, torch.Tensor) and out.shape == (5, 1000, 1000, 3)
+    assert (out.cpu().numpy() == want).all()
+    assert h16(out[0].cpu().numpy()) == fx.gold["native"]["blend1_balance0"]["car"]
+    # same buffers, new contents: the cached table is reused and must still be right
+    d_all.copy_(d_all.flip(0)); torch.cuda.synchronize()
+    out2 = torch.empty_like(out)
+    assert e.run_cuda(d_all, d_car, out=out2) is out2
+    stream.synchronize()
+    assert (out2.cpu().numpy() == want[::-1]).all()
+    # nested lists of separately allocated frames (a different table), balance, no car
+    nested = [[torch.from_numpy(f).to(dev) for f in s] for s in host_sets[:3]]
+    torch.cuda.synchronize()
+    out3 = e.run_cuda(nested, d_car, balance=True)
+    stream.synchronize()
+    assert (out3.cpu().numpy() == want_bal[:3]).all()
+    e.ctx.set_stream(None)        # back to the ctx's own stream: the cached table is dropped and re-uploaded
+    out4 = e.run_cuda(nested)
+    e.ctx.sync()
+    assert (out4.cpu().numpy() == e.run(host_sets[:3])).all()
+    with pytest.raises(L.BevkError, match="must be uint8"):
+        e.run_cuda(d_all.to(torch.float32))
+    skewed = nested[0][0].permute(1, 0, 2).contiguous().permute(1, 0, 2)      # right shape, wrong strides
+    with pytest.raises(L.BevkError, match="C-contiguous"):
+        e.run_cuda([[skewed] + nested[0][1:]])
+    with pytest.raises(L.BevkError, match="got"):
+        e.run_cuda(d_all[:, :3].contiguous())
+    with pytest.raises(L.BevkError, match="expected 4"):
+        e.run_cuda([nested[0][:3]])
+    with pytest.raises(L.BevkError, match="__cuda_array_interface__"):
+        e.run_cuda([[f for f in host_sets[0]]])
