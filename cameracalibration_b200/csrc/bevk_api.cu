@@ -181,10 +181,16 @@ int bevk_ctx_create(int device, bevk_ctx** out) {
   bevk_ctx* c = new (std::nothrow) bevk_ctx;
   if (!c) return fail(BEVK_ERR_OOM, "host allocation failed");
   c->device = device;
-  CU(cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking));
+  cudaError_t e1 = cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking);
+  cudaError_t e2 = e1 == cudaSuccess ? cudaEventCreate(&c->ev0) : e1;
+  cudaError_t e3 = e2 == cudaSuccess ? cudaEventCreate(&c->ev1) : e2;
+  if (e3 != cudaSuccess) {
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->own) cudaStreamDestroy(c->own);
+    delete c;
+    return fail(BEVK_ERR_CUDA, "context setup: %s", cudaGetErrorString(e3));
+  }
   c->stream = c->own;
-  CU(cudaEventCreate(&c->ev0));
-  CU(cudaEventCreate(&c->ev1));
   *out = c;
   return BEVK_OK;
 }
@@ -192,10 +198,10 @@ int bevk_ctx_create(int device, bevk_ctx** out) {
 int bevk_ctx_destroy(bevk_ctx* c) {
   if (!c) return BEVK_OK;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  cudaDeviceSynchronize();   // not c->stream: a caller-owned stream handed to bevk_ctx_set_stream may be gone by now
   for (DevBuf* b : {&c->s_src, &c->s_dst, &c->s_m1, &c->s_m2, &c->s_o1, &c->s_o2, &c->d_tiles, &c->d_items, &c->d_lut,
                     &c->d_hsv, &c->d_frames, &c->d_ptrs, &c->d_canvas, &c->d_car, &c->d_vsum, &c->d_delta, &c->d_csum,
-                    &c->d_spans, &c->d_bal, &c->d_bal_ptrs})
+                    &c->d_spans, &c->d_bal, &c->d_bal_ptrs, &c->d_user_ptrs})
     b->release();
   for (auto& u : c->und) { u.map1.release(); u.map2.release(); }
   for (auto& k : c->cam) { k.map1.release(); k.map2.release(); }
@@ -833,7 +839,11 @@ int bevk_bev_run_frames(bevk_ctx* c, const void* const* frames, int batch, const
     RET(c->d_user_ptrs.ensure(n * sizeof(void*)));
     c->user_tab.assign(frames, frames + n);
     // pageable source: the driver stages it before returning, and stream order protects launches still reading the old table
-    CU(cudaMemcpyAsync(c->d_user_ptrs.p, c->user_tab.data(), n * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+    const cudaError_t e = cudaMemcpyAsync(c->d_user_ptrs.p, c->user_tab.data(), n * sizeof(void*), cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) {
+      c->user_tab.clear();   // nothing cached: the next call uploads again
+      return fail(BEVK_ERR_CUDA, "frame table upload: %s", cudaGetErrorString(e));
+    }
   }
   c->timed = true;
   return run_device(c, c->d_user_ptrs.p, batch, d_car, flags, d_out, 0, BEVK_MAX_CAMERAS);
