@@ -62,20 +62,28 @@ __device__ __forceinline__ unsigned ldg32(const uint8_t* p) { return __ldg(reint
 #endif
 
 // Fast path, phase 2: the six words of one entry -> weighted pixel packed B | G<<8 | R<<16.
-__device__ __forceinline__ unsigned interp_fast(unsigned sh, unsigned wpx, unsigned wpy, unsigned wm, unsigned a0, unsigned a1,
-                                                unsigned a2, unsigned b0, unsigned b1, unsigned b2) {
-  const unsigned A = __funnelshift_r(a0, a1, sh), A2 = __funnelshift_r(a1, a2, sh);   // B0 G0 R0 B1 | G1 R1 . .
-  const unsigned B = __funnelshift_r(b0, b1, sh), B2 = __funnelshift_r(b1, b2, sh);
+__host__ __device__ __forceinline__ unsigned interp_fast(unsigned sh, unsigned wpx, unsigned wpy, unsigned wm, unsigned a0,
+                                                         unsigned a1, unsigned a2, unsigned b0, unsigned b1, unsigned b2) {
+  const unsigned A = lane_funnel_r(a0, a1, sh), A2 = lane_funnel_r(a1, a2, sh);   // B0 G0 R0 B1 | G1 R1 . .
+  const unsigned B = lane_funnel_r(b0, b1, sh), B2 = lane_funnel_r(b1, b2, sh);
   // four taps of one channel per register: [p00 p01 p10 p11]
-  const unsigned pb = __byte_perm(A, B, 0x7430);
-  const unsigned pg = __byte_perm(__byte_perm(A, A2, 0x0041), __byte_perm(B, B2, 0x0041), 0x5410);
-  const unsigned pr = __byte_perm(__byte_perm(A, A2, 0x0052), __byte_perm(B, B2, 0x0052), 0x5410);
-  const unsigned ob = __dp2a_hi(wpy, pb, __dp2a_lo(wpx, pb, 512u)) >> 10;
-  const unsigned og = __dp2a_hi(wpy, pg, __dp2a_lo(wpx, pg, 512u)) >> 10;
-  const unsigned orr = __dp2a_hi(wpy, pr, __dp2a_lo(wpx, pr, 512u)) >> 10;
+  const unsigned pb = lane_perm(A, B, 0x7430);
+  const unsigned pg = lane_perm(lane_perm(A, A2, 0x0041), lane_perm(B, B2, 0x0041), 0x5410);
+  const unsigned pr = lane_perm(lane_perm(A, A2, 0x0052), lane_perm(B, B2, 0x0052), 0x5410);
+  const unsigned ob = lane_dp2a_hi(wpy, pb, lane_dp2a_lo(wpx, pb, 512u)) >> 10;
+  const unsigned og = lane_dp2a_hi(wpy, pg, lane_dp2a_lo(wpx, pg, 512u)) >> 10;
+  const unsigned orr = lane_dp2a_hi(wpy, pr, lane_dp2a_lo(wpx, pr, 512u)) >> 10;
   // BlendMask.__call__ / Mask.__call__ in exact integer form (see header)
   // (v * wm) < 2^24 and the weighted value is its byte 2: pack the three byte-2s with two PRMTs
-  return __byte_perm(__byte_perm(ob * wm, og * wm, 0x0062), orr * wm, 0x7610);
+  return lane_perm(lane_perm(ob * wm, og * wm, 0x0062), orr * wm, 0x7610);
+}
+
+// Word w (0..23) of a packed-BGR tile row from its 32 BGRX accumulator words: bytes 4w..4w+3 of the row
+// start in pixel w + w/3 at byte phase w % 3.
+__host__ __device__ __forceinline__ unsigned tile_row_word(const unsigned* acc_row, int w) {
+  const int p = w + w / 3, ph = w - (w / 3) * 3;
+  const unsigned sel = ph == 0 ? 0x4210u : (ph == 1 ? 0x5421u : 0x6542u);
+  return lane_perm(acc_row[p], acc_row[p + 1], sel);
 }
 
 // Slow path (kept out of line so the hot loop stays inside the instruction cache): entries with
@@ -106,11 +114,11 @@ __device__ __noinline__ unsigned sample_slow(const SlowGeo P, const uint8_t* __r
 }
 
 // cv2.add of two packed BGR pixels: per-byte saturating add (bytes 0..2; byte 3 stays 0)
-__device__ __forceinline__ unsigned sat_add_bgr(unsigned a, unsigned b) {
+__host__ __device__ __forceinline__ unsigned sat_add_bgr(unsigned a, unsigned b) {
   const unsigned lo = (a & 0x00ff00ffu) + (b & 0x00ff00ffu);          // bytes 0 and 2 -> 9-bit sums in 16-bit lanes
   const unsigned hi = ((a >> 8) & 0xffu) + ((b >> 8) & 0xffu);        // byte 1
   const unsigned lo_s = (lo | (((lo >> 8) & 0x00010001u) * 0xffu)) & 0x00ff00ffu;
-  const unsigned hi_s = min(hi, 255u);
+  const unsigned hi_s = hi < 255u ? hi : 255u;
   return lo_s | (hi_s << 8);
 }
 
@@ -208,16 +216,13 @@ __global__ void __launch_bounds__(256, BEVK_MIN_CTAS) k_bev(BevParams P) {
         const int idx = i * 256 + t, r = idx / 24, w = idx - r * 24;     // word w of tile row r
         const int gy = tile.y + r;
         if (gy >= P.BH) continue;
-        const int p = w + w / 3, ph = w - (w / 3) * 3;                   // first pixel of the word, byte phase
-        const unsigned sel = ph == 0 ? 0x4210u : (ph == 1 ? 0x5421u : 0x6542u);
         const size_t word_off = ((size_t)gy * P.BW * 3 + (size_t)tile.x * 3) / 4 + w;
         const unsigned cw = P.car ? __ldg(reinterpret_cast<const unsigned*>(P.car) + word_off) : 0u;
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
           if (j >= nb) break;
-          const unsigned* a = acc + j * ACC_WORDS + r * ACC_WPITCH + p;
-          unsigned v = first ? 0u : __byte_perm(a[0], a[1], sel);
-          if (P.car) v = __vaddus4(v, cw);
+          unsigned v = first ? 0u : tile_row_word(acc + j * ACC_WORDS + r * ACC_WPITCH, w);
+          if (P.car) v = lane_addus4(v, cw);
           reinterpret_cast<unsigned*>(P.out + (size_t)(b0 + j) * P.canvas_bytes)[word_off] = v;
         }
       }
@@ -242,9 +247,9 @@ __global__ void __launch_bounds__(256, BEVK_MIN_CTAS) k_bev(BevParams P) {
       const unsigned* a = acc + j * ACC_WORDS + row * ACC_WPITCH + chunk * 4;
       unsigned x0 = a[0], x1 = a[1], x2 = a[2], x3 = a[3];                 // BGRX BGRX BGRX BGRX
       if (first) x0 = x1 = x2 = x3 = 0u;                                   // tile without a camera (car hole)
-      unsigned w0 = __byte_perm(x0, x1, 0x4210);                           // B0 G0 R0 B1
-      unsigned w1 = __byte_perm(x1, x2, 0x5421);                           // G1 R1 B2 G2
-      unsigned w2 = __byte_perm(x2, x3, 0x6542);                           // R2 B3 G3 R3
+      unsigned w0 = lane_perm(x0, x1, 0x4210);                             // B0 G0 R0 B1
+      unsigned w1 = lane_perm(x1, x2, 0x5421);                             // G1 R1 B2 G2
+      unsigned w2 = lane_perm(x2, x3, 0x6542);                             // R2 B3 G3 R3
       if (BAL) {   // channel sums of the composed canvas, before gains and car (surroundBEV.py:44-47)
         const unsigned px[4] = {x0, x1, x2, x3};
         unsigned sb = 0, sg = 0, sr = 0;
@@ -266,7 +271,7 @@ __global__ void __launch_bounds__(256, BEVK_MIN_CTAS) k_bev(BevParams P) {
       if (!inb) continue;
       uint8_t* o = P.out + (size_t)(b0 + j) * P.canvas_bytes + pix_off;
       if (full) {
-        if (!BAL && P.car) { w0 = __vaddus4(w0, c0); w1 = __vaddus4(w1, c1); w2 = __vaddus4(w2, c2); }
+        if (!BAL && P.car) { w0 = lane_addus4(w0, c0); w1 = lane_addus4(w1, c1); w2 = lane_addus4(w2, c2); }
         unsigned* g = reinterpret_cast<unsigned*>(o);
         g[0] = w0; g[1] = w1; g[2] = w2;
       } else {

@@ -108,8 +108,58 @@ __device__ __forceinline__ void warp_point(const Homog& hm, int x, int y, double
 
 __device__ __forceinline__ int sat_i16(int v) { return max(-32768, min(32767, v)); }
 
+// ---- byte-lane primitives with a host form ------------------------------------
+// The packed integer arithmetic of the gathers (interp_fast, sat_add_bgr, the tile write-out) is built from
+// these; on the device they are single SASS instructions (PRMT, SHF, IDP.2A, VADDUS4-style), on the host plain
+// C, so tests/host/kernel_math.cu can check the packed forms against the scalar definitions without a GPU.
+__host__ __device__ __forceinline__ unsigned lane_perm(unsigned a, unsigned b, unsigned sel) {
+#ifdef __CUDA_ARCH__
+  return __byte_perm(a, b, sel);
+#else
+  const unsigned long long v = ((unsigned long long)b << 32) | a;   // selector nibbles 0..7 only (no sign replication here)
+  unsigned r = 0;
+  for (int i = 0; i < 4; ++i) r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7u))) & 255u) << (8 * i);
+  return r;
+#endif
+}
+__host__ __device__ __forceinline__ unsigned lane_funnel_r(unsigned lo, unsigned hi, unsigned shift) {
+#ifdef __CUDA_ARCH__
+  return __funnelshift_r(lo, hi, shift);
+#else
+  shift &= 31u;
+  return shift ? (lo >> shift) | (hi << (32u - shift)) : lo;
+#endif
+}
+// two unsigned 16-bit weights (a) times the low / high byte pair of b, plus c
+__host__ __device__ __forceinline__ unsigned lane_dp2a_lo(unsigned a, unsigned b, unsigned c) {
+#ifdef __CUDA_ARCH__
+  return __dp2a_lo(a, b, c);
+#else
+  return c + (a & 0xffffu) * (b & 255u) + (a >> 16) * ((b >> 8) & 255u);
+#endif
+}
+__host__ __device__ __forceinline__ unsigned lane_dp2a_hi(unsigned a, unsigned b, unsigned c) {
+#ifdef __CUDA_ARCH__
+  return __dp2a_hi(a, b, c);
+#else
+  return c + (a & 0xffffu) * ((b >> 16) & 255u) + (a >> 16) * (b >> 24);
+#endif
+}
+__host__ __device__ __forceinline__ unsigned lane_addus4(unsigned a, unsigned b) {   // per-byte saturating add
+#ifdef __CUDA_ARCH__
+  return __vaddus4(a, b);
+#else
+  unsigned r = 0;
+  for (int i = 0; i < 4; ++i) {
+    const unsigned t = ((a >> (8 * i)) & 255u) + ((b >> (8 * i)) & 255u);
+    r |= (t > 255u ? 255u : t) << (8 * i);
+  }
+  return r;
+#endif
+}
+
 // A2: (sum w*p + 512) >> 10 with integer weights.
-__device__ __forceinline__ int bilerp_q10(int p00, int p01, int p10, int p11, int fx, int fy) {
+__host__ __device__ __forceinline__ int bilerp_q10(int p00, int p01, int p10, int p11, int fx, int fy) {
   const int w11 = fx * fy, w01 = (fx << 5) - w11, w10 = (fy << 5) - w11;
   const int w00 = 1024 - (fx << 5) - (fy << 5) + w11;
   return (w00 * p00 + w01 * p01 + w10 * p10 + w11 * p11 + 512) >> 10;

@@ -1,0 +1,123 @@
+// Host-side unit test of the kernels' packed integer arithmetic (no GPU, no CUDA runtime calls):
+// the __host__ __device__ helpers of bevk_device.cuh / bevk_bev.cuh against their scalar definitions.
+//   interp_fast      == per channel ((sum w*p + 512) >> 10) * (257*mask+1) >> 16   (cv2.remap INTER_LINEAR, surroundBEV.py:116-117,
+//                                                                                   then BlendMask.__call__ :279-280)
+//   sat_add_bgr      == per-byte min(a+b, 255)                                       (cv2.add, :318-320)
+//   tile_row_word    == byte packing of a BGRX accumulator row into dense BGR words  (canvas layout)
+//   lane_addus4      == per-byte saturating add                                      (car overlay, :323-324)
+// Built and run by tests/test_host_math.py with nvcc (host code only is executed).
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../cameracalibration_b200/csrc/bevk_bev.cuh"
+
+using namespace bevk;
+
+static uint64_t rng_state = 0x9e3779b97f4a7c15ull;
+static uint32_t rnd() {
+  rng_state ^= rng_state << 7; rng_state ^= rng_state >> 9; rng_state *= 0x2545f4914f6cdd1dull;
+  return (uint32_t)(rng_state >> 24);
+}
+
+static int fails = 0;
+#define CHECK(cond, ...)                                   \
+  do {                                                     \
+    if (!(cond)) {                                         \
+      if (fails < 10) { printf("FAIL %s:%d: ", __FILE__, __LINE__); printf(__VA_ARGS__); printf("\n"); } \
+      ++fails;                                             \
+    }                                                      \
+  } while (0)
+
+int main() {
+  // ---- interp_fast: every byte alignment, every fraction, random pixels and masks
+  long long n_interp = 0;
+  for (int align = 0; align < 4; ++align)
+    for (int fx = 0; fx < 32; ++fx)
+      for (int fy = 0; fy < 32; ++fy)
+        for (int rep = 0; rep < 24; ++rep) {
+          uint8_t rows[2][16];
+          for (auto& r : rows) for (auto& b : r) b = (uint8_t)rnd();
+          if (rep == 0) memset(rows, 255, sizeof rows);              // saturation / rounding stress
+          if (rep == 1) memset(rows, 0, sizeof rows);
+          const unsigned mask = rep < 4 ? (rep & 1 ? 255u : 0u) : (rnd() & 255u);
+          const unsigned wm = mask ? 257u * mask + 1u : 0u;           // plan compiler: mask 0 -> 0
+          unsigned w[2][3];
+          for (int r = 0; r < 2; ++r)
+            for (int k = 0; k < 3; ++k) memcpy(&w[r][k], rows[r] + 4 * k, 4);
+          const bool third = align == 3;
+          const unsigned w11 = fx * fy, w01 = (fx << 5) - w11, w10 = (fy << 5) - w11, w00 = 1024 - (fx << 5) - (fy << 5) + w11;
+          const unsigned got = interp_fast(align * 8, w00 | (w01 << 16), w10 | (w11 << 16), wm, w[0][0], w[0][1],
+                                           third ? w[0][2] : 0u, w[1][0], w[1][1], third ? w[1][2] : 0u);
+          unsigned want = 0;
+          for (int c = 0; c < 3; ++c) {
+            const int p00 = rows[0][align + c], p01 = rows[0][align + 3 + c], p10 = rows[1][align + c], p11 = rows[1][align + 3 + c];
+            const unsigned v = (unsigned)bilerp_q10(p00, p01, p10, p11, fx, fy);
+            const float fm = (float)((double)mask / 255.0);          // BlendMask weight as the reference forms it
+            const unsigned ref_blend = (unsigned)(uint8_t)((float)v * fm);
+            const unsigned mine = (v * wm) >> 16;
+            CHECK(mine == ref_blend, "blend identity v=%u mask=%u: %u vs %u", v, mask, mine, ref_blend);
+            want |= mine << (8 * c);
+          }
+          CHECK(got == want, "interp_fast align=%d fx=%d fy=%d mask=%u: %08x vs %08x", align, fx, fy, mask, got, want);
+          ++n_interp;
+        }
+  // ---- the blend identity exhaustively (256 x 256)
+  for (unsigned v = 0; v < 256; ++v)
+    for (unsigned m = 0; m < 256; ++m) {
+      const float fm = (float)((double)m / 255.0);
+      const unsigned wm = m ? 257u * m + 1u : 0u;
+      CHECK(((v * wm) >> 16) == (unsigned)(uint8_t)((float)v * fm), "identity v=%u m=%u", v, m);
+    }
+  // ---- sat_add_bgr / lane_addus4
+  for (int i = 0; i < 2000000; ++i) {
+    unsigned a = rnd() & 0x00ffffffu, b = rnd() & 0x00ffffffu;
+    if (i < 256) { a = 0x00ffffffu; b = (unsigned)i * 0x010101u; }
+    unsigned want = 0, want4 = 0;
+    const unsigned a4 = a | (rnd() << 24), b4 = b | (rnd() << 24);
+    for (int c = 0; c < 4; ++c) {
+      const unsigned s3 = ((a >> (8 * c)) & 255u) + ((b >> (8 * c)) & 255u);
+      const unsigned s4 = ((a4 >> (8 * c)) & 255u) + ((b4 >> (8 * c)) & 255u);
+      if (c < 3) want |= (s3 > 255u ? 255u : s3) << (8 * c);
+      want4 |= (s4 > 255u ? 255u : s4) << (8 * c);
+    }
+    CHECK(sat_add_bgr(a, b) == want, "sat_add_bgr %08x + %08x: %08x vs %08x", a, b, sat_add_bgr(a, b), want);
+    CHECK(lane_addus4(a4, b4) == want4, "lane_addus4 %08x + %08x", a4, b4);
+  }
+  // ---- tile_row_word and the 4-pixel write-out selectors: BGRX accumulator row -> dense BGR bytes
+  for (int rep = 0; rep < 2000; ++rep) {
+    unsigned acc[TILE + 1];
+    uint8_t dense[TILE * 3];
+    for (int p = 0; p < TILE; ++p) {
+      acc[p] = rnd() & 0x00ffffffu;
+      dense[3 * p] = acc[p] & 255u; dense[3 * p + 1] = (acc[p] >> 8) & 255u; dense[3 * p + 2] = (acc[p] >> 16) & 255u;
+    }
+    acc[TILE] = 0xdeadbeefu;   // the pad word of the 33-word pitch is never selected
+    for (int w = 0; w < 24; ++w) {
+      unsigned want;
+      memcpy(&want, dense + 4 * w, 4);
+      CHECK(tile_row_word(acc, w) == want, "tile_row_word w=%d", w);
+    }
+    for (int chunk = 0; chunk < 8; ++chunk) {   // the shipped write-out: thread = 4 pixels -> 3 words
+      const unsigned* a = acc + chunk * 4;
+      unsigned want[3];
+      memcpy(want, dense + 12 * chunk, 12);
+      CHECK(lane_perm(a[0], a[1], 0x4210) == want[0] && lane_perm(a[1], a[2], 0x5421) == want[1] &&
+            lane_perm(a[2], a[3], 0x6542) == want[2], "4-pixel write-out chunk=%d", chunk);
+    }
+  }
+  // ---- coalesced write-out index map (BEVK_WRITE_COALESCED): 3 x 256 threads cover 32 rows x 24 words exactly once
+  {
+    int seen[TILE][24] = {};
+    for (int i = 0; i < 3; ++i)
+      for (int t = 0; t < 256; ++t) {
+        const int idx = i * 256 + t, r = idx / 24, w = idx - r * 24;
+        CHECK(r < TILE && w < 24, "index map out of range");
+        seen[r][w]++;
+      }
+    for (int r = 0; r < TILE; ++r) for (int w = 0; w < 24; ++w) CHECK(seen[r][w] == 1, "word (%d,%d) written %d times", r, w, seen[r][w]);
+  }
+  printf("kernel_math: %lld interp cases, fails=%d\n", n_interp, fails);
+  return fails ? 1 : 0;
+}
