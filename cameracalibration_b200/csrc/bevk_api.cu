@@ -64,26 +64,6 @@ struct DevBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-// OpenCV's closed-form 3x3 inverse (cv::invert, DECOMP_LU, n == 3, CV_64F).
-static bool inv3(const double* S, double* T) {
-#define M(r, c) S[(r) * 3 + (c)]
-  double d = M(0, 0) * (M(1, 1) * M(2, 2) - M(1, 2) * M(2, 1)) - M(0, 1) * (M(1, 0) * M(2, 2) - M(1, 2) * M(2, 0)) +
-             M(0, 2) * (M(1, 0) * M(2, 1) - M(1, 1) * M(2, 0));
-  if (d == 0.) return false;
-  d = 1. / d;
-  T[0] = (M(1, 1) * M(2, 2) - M(1, 2) * M(2, 1)) * d;
-  T[1] = (M(0, 2) * M(2, 1) - M(0, 1) * M(2, 2)) * d;
-  T[2] = (M(0, 1) * M(1, 2) - M(0, 2) * M(1, 1)) * d;
-  T[3] = (M(1, 2) * M(2, 0) - M(1, 0) * M(2, 2)) * d;
-  T[4] = (M(0, 0) * M(2, 2) - M(0, 2) * M(2, 0)) * d;
-  T[5] = (M(0, 2) * M(1, 0) - M(0, 0) * M(1, 2)) * d;
-  T[6] = (M(1, 0) * M(2, 1) - M(1, 1) * M(2, 0)) * d;
-  T[7] = (M(0, 1) * M(2, 0) - M(0, 0) * M(2, 1)) * d;
-  T[8] = (M(0, 0) * M(1, 1) - M(0, 1) * M(1, 0)) * d;
-#undef M
-  return true;
-}
-
 static int make_model(int model, const double* K, const double* D, int n_dist, const double* P, int w, int h,
                       CamModel* cm) {
   if (!K || !P || (n_dist > 0 && !D)) return fail(BEVK_ERR_ARG, "null K/D/P");

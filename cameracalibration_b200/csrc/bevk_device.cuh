@@ -24,35 +24,69 @@ struct CamModel {      // cv2.fisheye / cv2 initUndistortRectifyMap inputs, pre-
 
 struct Homog { double M[9]; };   // inv(H), as cv2.warpPerspective computes it
 
+// OpenCV's closed-form 3x3 inverse (cv::invert, DECOMP_LU, n == 3, CV_64F).
+inline bool inv3(const double* S, double* T) {
+#define M(r, c) S[(r) * 3 + (c)]
+  double d = M(0, 0) * (M(1, 1) * M(2, 2) - M(1, 2) * M(2, 1)) - M(0, 1) * (M(1, 0) * M(2, 2) - M(1, 2) * M(2, 0)) +
+             M(0, 2) * (M(1, 0) * M(2, 1) - M(1, 1) * M(2, 0));
+  if (d == 0.) return false;
+  d = 1. / d;
+  T[0] = (M(1, 1) * M(2, 2) - M(1, 2) * M(2, 1)) * d;
+  T[1] = (M(0, 2) * M(2, 1) - M(0, 1) * M(2, 2)) * d;
+  T[2] = (M(0, 1) * M(1, 2) - M(0, 2) * M(1, 1)) * d;
+  T[3] = (M(1, 2) * M(2, 0) - M(1, 0) * M(2, 2)) * d;
+  T[4] = (M(0, 0) * M(2, 2) - M(0, 2) * M(2, 0)) * d;
+  T[5] = (M(0, 2) * M(1, 0) - M(0, 0) * M(1, 2)) * d;
+  T[6] = (M(1, 0) * M(2, 1) - M(1, 1) * M(2, 0)) * d;
+  T[7] = (M(0, 1) * M(2, 0) - M(0, 0) * M(2, 1)) * d;
+  T[8] = (M(0, 0) * M(1, 1) - M(0, 1) * M(1, 0)) * d;
+#undef M
+  return true;
+}
+
 // does undistorted pixel column j take the saturating (vector-body) pack?  (pinhole model only)
 __host__ __device__ __forceinline__ bool pack_saturates(int model, int j, int w) { return model == 1 && j < w - (w % 8); }
 
+// Separately rounded FP64 operations (no FMA contraction), as OpenCV's scalar C++ evaluates them.  The host
+// forms let tests/host/kernel_math.cu run the very same coordinate code on a CPU (built without contraction).
+#ifdef __CUDA_ARCH__
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
+__device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
+__device__ __forceinline__ int d2i_rn(double v) { return __double2int_rn(v); }
+#else
+inline double dmul(double a, double b) { volatile double r = a * b; return r; }
+inline double dadd(double a, double b) { volatile double r = a + b; return r; }
+inline double ddiv(double a, double b) { volatile double r = a / b; return r; }
+inline double dsqrt(double a) { return sqrt(a); }
+inline double dinf() { return HUGE_VAL; }
+inline int d2i_rn(double v) { return (int)nearbyint(v); }   // default rounding mode: to nearest even
+#endif
 
 // cvRound / saturate_cast<int>(double): x86 cvtsd2si returns INT_MIN ("integer
 // indefinite") for NaN and out-of-range inputs.
-__device__ __forceinline__ int cv_round(double v) {
+__host__ __device__ __forceinline__ int cv_round(double v) {
   if (!(fabs(v) < 2147483648.0)) return INT_MIN;
-  return __double2int_rn(v);
+  return d2i_rn(v);
 }
 
 // A1 / A11: source-image position (u,v) of undistorted pixel (j,i).
-__device__ __forceinline__ void undistort_point(const CamModel& c, int j, int i, double& u, double& v) {
+__host__ __device__ __forceinline__ void undistort_point(const CamModel& c, int j, int i, double& u, double& v) {
   const double dj = (double)j, di = (double)i;
   const double _x = dadd(dmul(dj, c.iR[0]), dadd(dmul(di, c.iR[1]), c.iR[2]));
   const double _y = dadd(dmul(dj, c.iR[3]), dadd(dmul(di, c.iR[4]), c.iR[5]));
   const double _w = dadd(dmul(dj, c.iR[6]), dadd(dmul(di, c.iR[7]), c.iR[8]));
   if (c.model == 0) {  // equidistant fisheye
     if (_w <= 0) {
-      const double inf = __longlong_as_double(0x7ff0000000000000LL);
+      const double inf = dinf();
       u = (_x > 0) ? -inf : inf;
       v = (_y > 0) ? -inf : inf;
       return;
     }
     const double x = ddiv(_x, _w), y = ddiv(_y, _w);
-    const double r = __dsqrt_rn(dadd(dmul(x, x), dmul(y, y)));
+    const double r = dsqrt(dadd(dmul(x, x), dmul(y, y)));
     const double th = atan(r);
     const double t2 = dmul(th, th), t4 = dmul(t2, t2), t6 = dmul(t4, t2), t8 = dmul(t4, t4);
     const double poly = dadd(dadd(dadd(dadd(1.0, dmul(c.k[0], t2)), dmul(c.k[1], t4)), dmul(c.k[2], t6)), dmul(c.k[3], t8));
@@ -77,7 +111,7 @@ __device__ __forceinline__ void undistort_point(const CamModel& c, int j, int i,
 // cast), map2 = (iv&31)*32 + (iu&31).
 // `saturate`: cv2.initUndistortRectifyMap's (pinhole) vector body packs with signed
 // saturation for columns j < W - W%8; everything else wraps like the C cast it is.
-__device__ __forceinline__ void quantise_uv(double u, double v, short& mx, short& my, unsigned short& frac,
+__host__ __device__ __forceinline__ void quantise_uv(double u, double v, short& mx, short& my, unsigned short& frac,
                                             bool saturate = false) {
   const int iu = cv_round(dmul(u, (double)TAB));
   const int iv = cv_round(dmul(v, (double)TAB));
@@ -89,7 +123,7 @@ __device__ __forceinline__ void quantise_uv(double u, double v, short& mx, short
 
 // A3: fixed-point pre-image of destination pixel (x,y) under cv2.warpPerspective.
 // unit = 32 for INTER_LINEAR, 1 for INTER_NEAREST.  OpenCV evaluates in 64-pixel blocks.
-__device__ __forceinline__ void warp_point(const Homog& hm, int x, int y, double unit, int& X, int& Y) {
+__host__ __device__ __forceinline__ void warp_point(const Homog& hm, int x, int y, double unit, int& X, int& Y) {
   const double* M = hm.M;
   const int bxi = (x >> 6) << 6;
   const double bx = (double)bxi, x1 = (double)(x - bxi), dy = (double)y;
@@ -106,7 +140,7 @@ __device__ __forceinline__ void warp_point(const Homog& hm, int x, int y, double
   Y = cv_round(fY);
 }
 
-__device__ __forceinline__ int sat_i16(int v) { return max(-32768, min(32767, v)); }
+__host__ __device__ __forceinline__ int sat_i16(int v) { return max(-32768, min(32767, v)); }
 
 // ---- byte-lane primitives with a host form ------------------------------------
 // The packed integer arithmetic of the gathers (interp_fast, sat_add_bgr, the tile write-out) is built from

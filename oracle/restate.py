@@ -164,10 +164,33 @@ def remap_nearest(src: np.ndarray, map1: np.ndarray, map2: np.ndarray | None) ->
 # A3  cv2.warpPerspective(src, H, (DW, DH))  (INTER_LINEAR, BORDER_CONSTANT 0)
 #     surroundBEV.py:113-114, extrinsicCalib.py:166-169
 # ----------------------------------------------------------------------------
+def invert3(S) -> np.ndarray:
+    """cv::invert of a 3x3 CV_64F matrix (DECOMP_LU takes the closed adjugate form for n <= 3; what
+    cv2.warpPerspective applies to H).  Bit-identical to ``cv2.invert(S)[1]``; ``np.linalg.inv`` (LAPACK) differs
+    in the last bits, enough to move about one 1/32-px coordinate per million.  Singular -> zeros."""
+    S = np.asarray(S, np.float64)
+    d = (S[0, 0] * (S[1, 1] * S[2, 2] - S[1, 2] * S[2, 1]) - S[0, 1] * (S[1, 0] * S[2, 2] - S[1, 2] * S[2, 0])
+         + S[0, 2] * (S[1, 0] * S[2, 1] - S[1, 1] * S[2, 0]))
+    T = np.zeros((3, 3))
+    if d == 0.0:
+        return T
+    d = 1.0 / d
+    T[0, 0] = (S[1, 1] * S[2, 2] - S[1, 2] * S[2, 1]) * d
+    T[0, 1] = (S[0, 2] * S[2, 1] - S[0, 1] * S[2, 2]) * d
+    T[0, 2] = (S[0, 1] * S[1, 2] - S[0, 2] * S[1, 1]) * d
+    T[1, 0] = (S[1, 2] * S[2, 0] - S[1, 0] * S[2, 2]) * d
+    T[1, 1] = (S[0, 0] * S[2, 2] - S[0, 2] * S[2, 0]) * d
+    T[1, 2] = (S[0, 2] * S[1, 0] - S[0, 0] * S[1, 2]) * d
+    T[2, 0] = (S[1, 0] * S[2, 1] - S[1, 1] * S[2, 0]) * d
+    T[2, 1] = (S[0, 1] * S[2, 0] - S[0, 0] * S[2, 1]) * d
+    T[2, 2] = (S[0, 0] * S[1, 1] - S[0, 1] * S[1, 0]) * d
+    return T
+
+
 def warp_coords(Hm, DW: int, DH: int, unit: float = TAB):
     """Fixed-point pre-image of every dst pixel (block form, 64-px blocks).  ``unit``
     is 32 for INTER_LINEAR (1/32 px) and 1 for INTER_NEAREST (whole pixels)."""
-    M = np.linalg.inv(np.asarray(Hm, np.float64)).ravel()
+    M = invert3(Hm).ravel()
     x = np.arange(DW, dtype=np.int64)[None, :]
     y = np.arange(DH, dtype=np.float64)[:, None]
     bx = ((x // 64) * 64).astype(np.float64)

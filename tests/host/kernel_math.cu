@@ -30,7 +30,63 @@ static int fails = 0;
     }                                                      \
   } while (0)
 
-int main() {
+// ---- coordinate modes: run the kernels' FP64 code (undistort_point / quantise_uv / warp_point, host forms) over a
+// whole map and dump it, so tests/test_host_math.py can compare with live cv2.
+//   kernel_math maps <model> <w> <h> <out.bin>   stdin: K[9] D[5] P[9] as C99 hex floats
+//   kernel_math warp <w> <h> <unit> <out.bin>    stdin: H[9]
+static bool read_doubles(double* v, int n) {
+  for (int i = 0; i < n; ++i) {
+    char tok[64];
+    if (scanf("%63s", tok) != 1) return false;
+    v[i] = strtod(tok, nullptr);
+  }
+  return true;
+}
+
+static int mode_maps(int model, int w, int h, const char* path) {
+  double K[9], D[5], P[9];
+  if (!read_doubles(K, 9) || !read_doubles(D, 5) || !read_doubles(P, 9)) return 2;
+  CamModel cm;
+  memset(&cm, 0, sizeof cm);
+  if (!inv3(P, cm.iR)) return 3;
+  for (int i = 0; i < (model == 0 ? 4 : 5); ++i) cm.k[i] = D[i];
+  cm.fx = K[0]; cm.fy = K[4]; cm.cx = K[2]; cm.cy = K[5];
+  cm.model = model; cm.w = w; cm.h = h;
+  FILE* f = fopen(path, "wb");
+  if (!f) return 4;
+  short* m1 = (short*)malloc((size_t)w * h * 4);
+  unsigned short* m2 = (unsigned short*)malloc((size_t)w * h * 2);
+  for (int i = 0; i < h; ++i)
+    for (int j = 0; j < w; ++j) {
+      double u, v;
+      undistort_point(cm, j, i, u, v);
+      const size_t q = (size_t)i * w + j;
+      quantise_uv(u, v, m1[2 * q], m1[2 * q + 1], m2[q], pack_saturates(model, j, w));
+    }
+  fwrite(m1, 4, (size_t)w * h, f);
+  fwrite(m2, 2, (size_t)w * h, f);
+  fclose(f);
+  return 0;
+}
+
+static int mode_warp(int w, int h, double unit, const char* path) {
+  double H[9];
+  if (!read_doubles(H, 9)) return 2;
+  Homog hm;
+  if (!inv3(H, hm.M)) memset(hm.M, 0, sizeof hm.M);
+  FILE* f = fopen(path, "wb");
+  if (!f) return 4;
+  int* xy = (int*)malloc((size_t)w * h * 8);
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) warp_point(hm, x, y, unit, xy[2 * ((size_t)y * w + x)], xy[2 * ((size_t)y * w + x) + 1]);
+  fwrite(xy, 8, (size_t)w * h, f);
+  fclose(f);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc == 6 && !strcmp(argv[1], "maps")) return mode_maps(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5]);
+  if (argc == 6 && !strcmp(argv[1], "warp")) return mode_warp(atoi(argv[2]), atoi(argv[3]), atof(argv[4]), argv[5]);
   // ---- interp_fast: every byte alignment, every fraction, random pixels and masks
   long long n_interp = 0;
   for (int align = 0; align < 4; ++align)

@@ -1,31 +1,100 @@
-"""The kernels' packed integer arithmetic, unit-tested on the CPU: tests/host/kernel_math.cu includes the
-__host__ __device__ helpers of the CUDA sources (interp_fast, sat_add_bgr, tile_row_word, lane_*) and checks them
-against the scalar definitions of cv2.remap / BlendMask / cv2.add.  nvcc compiles it; only host code runs."""
+"""The kernels' arithmetic, unit-tested on the CPU.  tests/host/kernel_math.cu includes the __host__ __device__
+helpers of the CUDA sources and (a) checks the packed integer forms (interp_fast, sat_add_bgr, tile_row_word, lane_*)
+against the scalar definitions of cv2.remap / BlendMask / cv2.add, (b) runs the FP64 coordinate code
+(undistort_point, quantise_uv, warp_point, the closed-form 3x3 inverse) over whole maps, compared here with live cv2.
+nvcc compiles it; only host code runs (no GPU, no CUDA runtime call)."""
 import os
 import shutil
 import subprocess
 
+import cv2
+import numpy as np
 import pytest
+
+from oracle import cv2_path as C
+from oracle import restate as R
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _nvcc():
-    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
-        if cand and os.path.exists(cand):
-            return cand
-    return None
-
-
-def test_packed_kernel_arithmetic_on_the_host(tmp_path):
-    nvcc = _nvcc()
+@pytest.fixture(scope="module")
+def exe(tmp_path_factory):
+    nvcc = next((c for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc") if c and os.path.exists(c)), None)
     if nvcc is None:
         pytest.skip("nvcc not found")
-    exe = tmp_path / "kernel_math"
+    out = tmp_path_factory.mktemp("host_math") / "kernel_math"
     src = os.path.join(ROOT, "tests", "host", "kernel_math.cu")
-    build = subprocess.run([nvcc, "-O2", "-std=c++17", "--fmad=false", "-gencode", "arch=compute_100a,code=sm_100a",
-                            "-o", str(exe), src], capture_output=True, text=True, timeout=600)
+    # no FMA contraction on the host side either (x86-64 baseline has none; the flag makes it explicit)
+    build = subprocess.run([nvcc, "-O2", "-std=c++17", "--fmad=false", "-Xcompiler", "-ffp-contract=off", "-gencode",
+                            "arch=compute_100a,code=sm_100a", "-o", str(out), src], capture_output=True, text=True, timeout=600)
     assert build.returncode == 0, build.stdout + build.stderr
-    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    return str(out)
+
+
+def _run(exe, args, values):
+    text = " ".join(float(v).hex() for v in values)
+    r = subprocess.run([exe] + [str(a) for a in args], input=text, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+
+
+def _maps(exe, tmp_path, model, K, D, P, w, h):
+    d = np.zeros(5)
+    dd = np.asarray(D, np.float64).ravel()
+    d[:dd.size] = dd
+    out = tmp_path / "maps.bin"
+    _run(exe, ["maps", model, w, h, out], list(np.asarray(K, np.float64).ravel()) + list(d) + list(np.asarray(P, np.float64).ravel()))
+    raw = np.fromfile(out, np.uint8)
+    m1 = raw[:w * h * 4].view(np.int16).reshape(h, w, 2)
+    m2 = raw[w * h * 4:].view(np.uint16).reshape(h, w)
+    return m1, m2
+
+
+def test_packed_kernel_arithmetic_on_the_host(exe):
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert run.returncode == 0, run.stdout + run.stderr
     assert "fails=0" in run.stdout
+
+
+def test_fisheye_and_pinhole_map_code_on_the_host(exe, tmp_path, fx):
+    K, D, _ = fx.calib["front"]
+    for (w, h, FS, SS) in ((1280, 1024, 0.5, 1), (2560, 2048, 1, 2)):     # InCalibrator / Camera geometries
+        P = C.dst_camera_matrix(K, 1280, 1024, FS, SS)
+        got, want = _maps(exe, tmp_path, 0, K, D, P, w, h), C.undistort_maps(K, D, P, w, h)
+        assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
+    rng = np.random.default_rng(11)
+    for _ in range(4):
+        W, H = int(rng.integers(64, 500)), int(rng.integers(48, 400))
+        Kr = np.array([[rng.uniform(80, 500), 0, W / 2 + rng.uniform(-20, 20)], [0, rng.uniform(80, 500), H / 2 + rng.uniform(-20, 20)],
+                       [0, 0, 1.0]])
+        P = C.dst_camera_matrix(Kr, W, H, rng.uniform(0.3, 1.5), 1, rng.uniform(-9, 9), rng.uniform(-9, 9))
+        Dr = rng.uniform(-0.05, 0.05, (4, 1))
+        got, want = _maps(exe, tmp_path, 0, Kr, Dr, P, W, H), C.undistort_maps(Kr, Dr, P, W, H)
+        assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
+        D5 = np.array([rng.uniform(-0.3, 0.1), rng.uniform(-0.05, 0.1), rng.uniform(-1e-3, 1e-3), rng.uniform(-1e-3, 1e-3),
+                       rng.uniform(-0.02, 0.02)])
+        got, want = _maps(exe, tmp_path, 1, Kr, D5, P, W, H), C.pinhole_maps(Kr, D5[None, :], P, W, H)
+        assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
+
+
+def test_warp_point_code_on_the_host(exe, tmp_path, fx):
+    rng = np.random.default_rng(12)
+    cases = [(fx.calib[n][2], 1000, 1000) for n in ("front", "left")]
+    cases += [(np.eye(3) + rng.normal(0, [[0.3, 0.3, 40], [0.3, 0.3, 40], [6e-4, 6e-4, 0]]), 333, 177) for _ in range(3)]
+    for Hm, w, h in cases:
+        for unit in (32, 1):
+            out = tmp_path / "warp.bin"
+            _run(exe, ["warp", w, h, unit, out], list(np.asarray(Hm, np.float64).ravel()))
+            xy = np.fromfile(out, np.int32).reshape(h, w, 2)
+            X, Y = R.warp_coords(Hm, w, h, unit)
+            assert (xy[..., 0] == X).all() and (xy[..., 1] == Y).all()
+    # the coordinates are what cv2.warpPerspective itself uses: nearest-neighbour warp of an index image
+    Hm = fx.calib["back"][2]
+    out = tmp_path / "warp.bin"
+    _run(exe, ["warp", 400, 300, 1, out], list(Hm.ravel()))
+    xy = np.fromfile(out, np.int32).reshape(300, 400, 2)
+    idx = (np.arange(2048 * 2560, dtype=np.int64) % 251).astype(np.uint8).reshape(2048, 2560)
+    want = cv2.warpPerspective(idx, Hm, (400, 300), flags=cv2.INTER_NEAREST)
+    sx, sy = xy[..., 0], xy[..., 1]
+    inside = (sx >= 0) & (sx < 2560) & (sy >= 0) & (sy < 2048)
+    got = np.where(inside, idx[np.clip(sy, 0, 2047), np.clip(sx, 0, 2559)], 0)
+    assert (got == want).all()

@@ -64,3 +64,16 @@ def test_random_remap_and_compose(seed):
     w = (np.repeat(mask[:, :, None], 3, axis=2) / 255.0).astype(np.float32)
     assert (R.apply_blend(a, mask) == (a * w).astype(np.uint8)).all()
     assert (R.color_balance(a) == C.color_balance(a.copy())).all()
+
+
+def test_invert3_is_cv2_invert():
+    """cv2.warpPerspective inverts H with cv::invert's closed 3x3 form; LAPACK's inverse differs in the last bits
+    (found by tests/test_host_math.py: about one 1/32-px coordinate per million moved)."""
+    rng = np.random.default_rng(400)
+    differs = 0
+    for _ in range(300):
+        Hm = np.eye(3) + rng.normal(0, [[0.3, 0.3, 40], [0.3, 0.3, 40], [6e-4, 6e-4, 0]])
+        assert (R.invert3(Hm) == cv2.invert(Hm)[1]).all()
+        differs += int((np.linalg.inv(Hm) != cv2.invert(Hm)[1]).any())
+    assert differs > 0                                   # the distinction is real
+    assert (R.invert3(np.zeros((3, 3))) == 0).all()      # singular: zeros, as cv::invert leaves them
