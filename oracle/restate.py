@@ -101,7 +101,7 @@ def pinhole_map(K, D5, P, W: int, H: int):
     dd = np.asarray(D5, np.float64).ravel()
     d[:min(5, dd.size)] = dd[:5]
     k1, k2, p1, p2, k3 = d
-    ir = np.linalg.inv(np.asarray(P, np.float64))
+    ir = invert3(P)     # cv::Matx33d::inv(DECOMP_LU): the closed 3x3 form
     _x, _y, _w = _ray_terms(ir, W, H, running=True)
     w = 1.0 / _w
     x = _x * w
