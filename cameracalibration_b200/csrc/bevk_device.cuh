@@ -56,6 +56,10 @@ __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a,
 __device__ __forceinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
 __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
 __device__ __forceinline__ int d2i_rn(double v) { return __double2int_rn(v); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ int f2i_rn(float v) { return __float2int_rn(v); }
 #else
 inline double dmul(double a, double b) { volatile double r = a * b; return r; }
 inline double dadd(double a, double b) { volatile double r = a + b; return r; }
@@ -63,6 +67,10 @@ inline double ddiv(double a, double b) { volatile double r = a / b; return r; }
 inline double dsqrt(double a) { return sqrt(a); }
 inline double dinf() { return HUGE_VAL; }
 inline int d2i_rn(double v) { return (int)nearbyint(v); }   // default rounding mode: to nearest even
+inline float fmul(float a, float b) { volatile float r = a * b; return r; }
+inline float fsub(float a, float b) { volatile float r = a - b; return r; }
+inline float ffma(float a, float b, float c) { return fmaf(a, b, c); }
+inline int f2i_rn(float v) { return (int)nearbyintf(v); }
 #endif
 
 // cvRound / saturate_cast<int>(double): x86 cvtsd2si returns INT_MIN ("integer
@@ -203,7 +211,7 @@ __host__ __device__ __forceinline__ int bilerp_q10(int p00, int p01, int p10, in
 // sdiv[i] = cvRound((255<<12)/i), hdiv[i] = cvRound((180<<12)/(6 i)); filled on the host.
 struct HsvTables { int sdiv[256]; int hdiv[256]; };
 
-__device__ __forceinline__ void hsv_roundtrip(int& b, int& g, int& r, int delta, bool rounding_tail,
+__host__ __device__ __forceinline__ void hsv_roundtrip(int& b, int& g, int& r, int delta, bool rounding_tail,
                                               const int* __restrict__ sdiv, const int* __restrict__ hdiv) {
   const int v = max(b, max(g, r)), mn = min(b, min(g, r));
   const int d = v - mn;
@@ -213,17 +221,17 @@ __device__ __forceinline__ void hsv_roundtrip(int& b, int& g, int& r, int delta,
   if (hh < 0) hh += 180;
   const int v2 = max(0, min(255, v + delta));
   // HSV2BGR, OpenCV's vector body: fp32 with these exact FMA contractions, truncation.
-  const float sf = __fmul_rn((float)s, 1.0f / 255.0f);
-  const float vf = __fmul_rn((float)v2, 1.0f / 255.0f);
-  const float hx = __fmul_rn((float)hh, 6.0f / 180.0f);
+  const float sf = fmul((float)s, 1.0f / 255.0f);
+  const float vf = fmul((float)v2, 1.0f / 255.0f);
+  const float hx = fmul((float)hh, 6.0f / 180.0f);
   const float secf = truncf(hx);
-  const float f = __fsub_rn(hx, secf);
+  const float f = fsub(hx, secf);
   int sec = (int)secf;
   sec = sec % 6;
   const float t0 = vf;
-  const float t1 = __fmul_rn(vf, __fsub_rn(1.0f, sf));
-  const float t2 = __fmul_rn(vf, __fmaf_rn(-sf, f, 1.0f));
-  const float t3 = __fmul_rn(vf, __fmaf_rn(-sf, __fsub_rn(1.0f, f), 1.0f));
+  const float t1 = fmul(vf, fsub(1.0f, sf));
+  const float t2 = fmul(vf, ffma(-sf, f, 1.0f));
+  const float t3 = fmul(vf, ffma(-sf, fsub(1.0f, f), 1.0f));
   float fb, fg, fr;
   switch (sec) {   // sector table {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0}
     case 0: fb = t1; fg = t3; fr = t0; break;
@@ -233,11 +241,11 @@ __device__ __forceinline__ void hsv_roundtrip(int& b, int& g, int& r, int delta,
     case 4: fb = t0; fg = t1; fr = t3; break;
     default: fb = t2; fg = t1; fr = t0; break;
   }
-  fb = __fmul_rn(fb, 255.0f); fg = __fmul_rn(fg, 255.0f); fr = __fmul_rn(fr, 255.0f);
+  fb = fmul(fb, 255.0f); fg = fmul(fg, 255.0f); fr = fmul(fr, 255.0f);
   if (rounding_tail) {   // the < 32-pixel row tail goes through OpenCV's scalar path, which rounds
-    b = max(0, min(255, __float2int_rn(fb)));
-    g = max(0, min(255, __float2int_rn(fg)));
-    r = max(0, min(255, __float2int_rn(fr)));
+    b = max(0, min(255, f2i_rn(fb)));
+    g = max(0, min(255, f2i_rn(fg)));
+    r = max(0, min(255, f2i_rn(fr)));
   } else {
     b = max(0, min(255, (int)fb));
     g = max(0, min(255, (int)fg));

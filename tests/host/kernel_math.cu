@@ -84,7 +84,30 @@ static int mode_warp(int w, int h, double unit, const char* path) {
   return 0;
 }
 
+//   kernel_math hsv <delta> <tail 0|1> <out.bin>   all 2^24 BGR colours through hsv_roundtrip (luminance_balance's
+//                                                  8-bit HSV round trip), colour index = b | g<<8 | r<<16
+static int mode_hsv(int delta, int tail, const char* path) {
+  static int sdiv[256], hdiv[256];   // as bevk_bev_finalize fills them (OpenCV's sdiv_table / hdiv_table180)
+  sdiv[0] = hdiv[0] = 0;
+  for (int i = 1; i < 256; ++i) {
+    sdiv[i] = (int)nearbyint((255 << 12) / (1. * i));
+    hdiv[i] = (int)nearbyint((180 << 12) / (6. * i));
+  }
+  FILE* f = fopen(path, "wb");
+  if (!f) return 4;
+  uint8_t* out = (uint8_t*)malloc((size_t)3 << 24);
+  for (int c = 0; c < (1 << 24); ++c) {
+    int b = c & 255, g = (c >> 8) & 255, r = c >> 16;
+    hsv_roundtrip(b, g, r, delta, tail != 0, sdiv, hdiv);
+    out[3 * (size_t)c] = (uint8_t)b; out[3 * (size_t)c + 1] = (uint8_t)g; out[3 * (size_t)c + 2] = (uint8_t)r;
+  }
+  fwrite(out, 3, (size_t)1 << 24, f);
+  fclose(f);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc == 5 && !strcmp(argv[1], "hsv")) return mode_hsv(atoi(argv[2]), atoi(argv[3]), argv[4]);
   if (argc == 6 && !strcmp(argv[1], "maps")) return mode_maps(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5]);
   if (argc == 6 && !strcmp(argv[1], "warp")) return mode_warp(atoi(argv[2]), atoi(argv[3]), atof(argv[4]), argv[5]);
   // ---- interp_fast: every byte alignment, every fraction, random pixels and masks

@@ -98,3 +98,31 @@ def test_warp_point_code_on_the_host(exe, tmp_path, fx):
     inside = (sx >= 0) & (sx < 2560) & (sy >= 0) & (sy < 2048)
     got = np.where(inside, idx[np.clip(sy, 0, 2047), np.clip(sx, 0, 2559)], 0)
     assert (got == want).all()
+
+
+def test_hsv_round_trip_code_on_the_host_all_colours(exe, tmp_path):
+    """luminance_balance's 8-bit BGR -> HSV -> V+delta -> BGR (surroundBEV.py:57-79) for every one of the 2^24 colours:
+    the kernels' hsv_roundtrip (host form) against cv2.cvtColor itself -- OpenCV's 32-pixel vector body (truncating)
+    on a 4096-wide image, its scalar row tail (rounding) on 31-wide rows."""
+    c = np.arange(1 << 24, dtype=np.uint32)
+    colours = np.stack([c & 255, (c >> 8) & 255, c >> 16], axis=-1).astype(np.uint8)
+
+    def cv2_round_trip(img, delta):
+        h, s, v = cv2.split(cv2.cvtColor(img, cv2.COLOR_BGR2HSV))
+        v = cv2.add(v, float(delta))                                            # the reference's saturating V shift (:74)
+        return cv2.cvtColor(cv2.merge([h, s, v]), cv2.COLOR_HSV2BGR)
+
+    for delta in (0, 6, -6, 100, -200):
+        out = tmp_path / "hsv.bin"
+        r = subprocess.run([exe, "hsv", str(delta), "0", str(out)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0
+        got = np.fromfile(out, np.uint8).reshape(-1, 3)
+        want = cv2_round_trip(colours.reshape(4096, 4096, 3), delta).reshape(-1, 3)
+        assert (got == want).all(), (delta, int((got != want).any(axis=1).sum()))
+    # scalar tail: rows of 31 pixels never enter the vector body
+    n = (1 << 24) // 31 * 31
+    out = tmp_path / "hsv_tail.bin"
+    assert subprocess.run([exe, "hsv", "-6", "1", str(out)], capture_output=True, text=True, timeout=600).returncode == 0
+    got = np.fromfile(out, np.uint8).reshape(-1, 3)[:n]
+    want = cv2_round_trip(colours[:n].reshape(-1, 31, 3), -6).reshape(-1, 3)
+    assert (got == want).all(), int((got != want).any(axis=1).sum())
