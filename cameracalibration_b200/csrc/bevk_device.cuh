@@ -58,6 +58,7 @@ __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000
 __device__ __forceinline__ int d2i_rn(double v) { return __double2int_rn(v); }
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 __device__ __forceinline__ int f2i_rn(float v) { return __float2int_rn(v); }
 #else
@@ -69,6 +70,7 @@ inline double dinf() { return HUGE_VAL; }
 inline int d2i_rn(double v) { return (int)nearbyint(v); }   // default rounding mode: to nearest even
 inline float fmul(float a, float b) { volatile float r = a * b; return r; }
 inline float fsub(float a, float b) { volatile float r = a - b; return r; }
+inline float fadd(float a, float b) { volatile float r = a + b; return r; }
 inline float ffma(float a, float b, float c) { return fmaf(a, b, c); }
 inline int f2i_rn(float v) { return (int)nearbyintf(v); }
 #endif

@@ -124,18 +124,16 @@ struct WarpMapsArgs {
   short2* out1; unsigned short* out2; int dw, dh;
 };
 
+// One destination pixel of that warp (host-capable: tests/host/kernel_math.cu runs it on a CPU against cv2).
 template <int FROM_MODEL>
-__global__ void __launch_bounds__(256) k_warp_maps(WarpMapsArgs a) {
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= a.dw || y >= a.dh) return;
+__host__ __device__ __forceinline__ void warp_maps_pixel(const WarpMapsArgs& a, int x, int y, short& ox, short& oy,
+                                                         unsigned short& of) {
   int X, Y;
   warp_point(a.hm, x, y, (double)TAB, X, Y);
   const int sx = sat_i16(X >> INTER_BITS), sy = sat_i16(Y >> INTER_BITS);
-  const float ax = __fmul_rn((float)(X & (TAB - 1)), 1.0f / TAB);
-  const float ay = __fmul_rn((float)(Y & (TAB - 1)), 1.0f / TAB);
-  const float w[4] = {__fmul_rn(__fsub_rn(1.f, ay), __fsub_rn(1.f, ax)), __fmul_rn(__fsub_rn(1.f, ay), ax),
-                      __fmul_rn(ay, __fsub_rn(1.f, ax)), __fmul_rn(ay, ax)};
+  const float ax = fmul((float)(X & (TAB - 1)), 1.0f / TAB);
+  const float ay = fmul((float)(Y & (TAB - 1)), 1.0f / TAB);
+  const float w[4] = {fmul(fsub(1.f, ay), fsub(1.f, ax)), fmul(fsub(1.f, ay), ax), fmul(ay, fsub(1.f, ax)), fmul(ay, ax)};
   float accx = 0.f, accy = 0.f, accf = 0.f;
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
@@ -156,16 +154,30 @@ __global__ void __launch_bounds__(256) k_warp_maps(WarpMapsArgs a) {
       vx = (float)mx; vy = (float)my; vf = (float)fr;
     }
     // acc = ((t0*w0 + t1*w1) + t2*w2) + t3*w3, each product and sum rounded (no FMA)
-    if (t == 0) { accx = __fmul_rn(vx, w[0]); accy = __fmul_rn(vy, w[0]); accf = __fmul_rn(vf, w[0]); }
+    if (t == 0) { accx = fmul(vx, w[0]); accy = fmul(vy, w[0]); accf = fmul(vf, w[0]); }
     else {
-      accx = __fadd_rn(accx, __fmul_rn(vx, w[t]));
-      accy = __fadd_rn(accy, __fmul_rn(vy, w[t]));
-      accf = __fadd_rn(accf, __fmul_rn(vf, w[t]));
+      accx = fadd(accx, fmul(vx, w[t]));
+      accy = fadd(accy, fmul(vy, w[t]));
+      accf = fadd(accf, fmul(vf, w[t]));
     }
   }
+  ox = (short)sat_i16(f2i_rn(accx));
+  oy = (short)sat_i16(f2i_rn(accy));
+  const int fi = f2i_rn(accf);
+  of = (unsigned short)(fi < 0 ? 0 : (fi > 65535 ? 65535 : fi));
+}
+
+template <int FROM_MODEL>
+__global__ void __launch_bounds__(256) k_warp_maps(WarpMapsArgs a) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= a.dw || y >= a.dh) return;
+  short ox, oy;
+  unsigned short of;
+  warp_maps_pixel<FROM_MODEL>(a, x, y, ox, oy, of);
   const size_t o = (size_t)y * a.dw + x;
-  a.out1[o] = make_short2((short)sat_i16(__float2int_rn(accx)), (short)sat_i16(__float2int_rn(accy)));
-  a.out2[o] = (unsigned short)max(0, min(65535, __float2int_rn(accf)));
+  a.out1[o] = make_short2(ox, oy);
+  a.out2[o] = of;
 }
 
 // ---------------------------------------------------------------------------------

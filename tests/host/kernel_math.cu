@@ -12,6 +12,7 @@
 #include <cstring>
 
 #include "../../cameracalibration_b200/csrc/bevk_bev.cuh"
+#include "../../cameracalibration_b200/csrc/bevk_kernels.cuh"
 
 using namespace bevk;
 
@@ -106,7 +107,68 @@ static int mode_hsv(int delta, int tail, const char* path) {
   return 0;
 }
 
+//   kernel_math bevmaps <und_w> <und_h> <bw> <bh> <out.bin>   stdin: K[9] D[4] P[9] H[9]
+//       Camera.get_bev_maps (surroundBEV.py:105-108) the way bevk_bev_set_camera builds it: k_warp_maps<1>, i.e. the
+//       undistort map evaluated at the four taps of every canvas pixel, never materialised
+//   kernel_math warpmaps <sw> <sh> <dw> <dh> <in.bin> <out.bin> stdin: H[9]   (k_warp_maps<0>: planes given)
+static int write_planes(const char* path, const short* m1, const unsigned short* m2, size_t n) {
+  FILE* f = fopen(path, "wb");
+  if (!f) return 4;
+  fwrite(m1, 4, n, f);
+  fwrite(m2, 2, n, f);
+  fclose(f);
+  return 0;
+}
+
+static int mode_bevmaps(int uw, int uh, int bw, int bh, const char* path) {
+  double K[9], D[4], P[9], H[9];
+  if (!read_doubles(K, 9) || !read_doubles(D, 4) || !read_doubles(P, 9) || !read_doubles(H, 9)) return 2;
+  WarpMapsArgs a;
+  memset(&a, 0, sizeof a);
+  if (!inv3(P, a.cm.iR)) return 3;
+  for (int i = 0; i < 4; ++i) a.cm.k[i] = D[i];
+  a.cm.fx = K[0]; a.cm.fy = K[4]; a.cm.cx = K[2]; a.cm.cy = K[5];
+  a.cm.model = 0; a.cm.w = uw; a.cm.h = uh;
+  if (!inv3(H, a.hm.M)) memset(a.hm.M, 0, sizeof a.hm.M);
+  a.sw = uw; a.sh = uh; a.dw = bw; a.dh = bh;
+  const size_t n = (size_t)bw * bh;
+  short* m1 = (short*)malloc(n * 4);
+  unsigned short* m2 = (unsigned short*)malloc(n * 2);
+  for (int y = 0; y < bh; ++y)
+    for (int x = 0; x < bw; ++x) {
+      const size_t q = (size_t)y * bw + x;
+      warp_maps_pixel<1>(a, x, y, m1[2 * q], m1[2 * q + 1], m2[q]);
+    }
+  return write_planes(path, m1, m2, n);
+}
+
+static int mode_warpmaps(int sw, int sh, int dw, int dh, const char* in_path, const char* out_path) {
+  double H[9];
+  if (!read_doubles(H, 9)) return 2;
+  const size_t ns = (size_t)sw * sh, nd = (size_t)dw * dh;
+  short2* i1 = (short2*)malloc(ns * 4);
+  unsigned short* i2 = (unsigned short*)malloc(ns * 2);
+  FILE* f = fopen(in_path, "rb");
+  if (!f || fread(i1, 4, ns, f) != ns || fread(i2, 2, ns, f) != ns) return 5;
+  fclose(f);
+  WarpMapsArgs a;
+  memset(&a, 0, sizeof a);
+  if (!inv3(H, a.hm.M)) memset(a.hm.M, 0, sizeof a.hm.M);
+  a.in1 = i1; a.in2 = i2; a.sw = sw; a.sh = sh; a.dw = dw; a.dh = dh;
+  short* m1 = (short*)malloc(nd * 4);
+  unsigned short* m2 = (unsigned short*)malloc(nd * 2);
+  for (int y = 0; y < dh; ++y)
+    for (int x = 0; x < dw; ++x) {
+      const size_t q = (size_t)y * dw + x;
+      warp_maps_pixel<0>(a, x, y, m1[2 * q], m1[2 * q + 1], m2[q]);
+    }
+  return write_planes(out_path, m1, m2, nd);
+}
+
 int main(int argc, char** argv) {
+  if (argc == 7 && !strcmp(argv[1], "bevmaps")) return mode_bevmaps(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argv[6]);
+  if (argc == 8 && !strcmp(argv[1], "warpmaps"))
+    return mode_warpmaps(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argv[6], argv[7]);
   if (argc == 5 && !strcmp(argv[1], "hsv")) return mode_hsv(atoi(argv[2]), atoi(argv[3]), argv[4]);
   if (argc == 6 && !strcmp(argv[1], "maps")) return mode_maps(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5]);
   if (argc == 6 && !strcmp(argv[1], "warp")) return mode_warp(atoi(argv[2]), atoi(argv[3]), atof(argv[4]), argv[5]);

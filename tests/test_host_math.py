@@ -126,3 +126,31 @@ def test_hsv_round_trip_code_on_the_host_all_colours(exe, tmp_path):
     got = np.fromfile(out, np.uint8).reshape(-1, 3)[:n]
     want = cv2_round_trip(colours[:n].reshape(-1, 31, 3), -6).reshape(-1, 3)
     assert (got == want).all(), int((got != want).any(axis=1).sum())
+
+
+def test_bev_lut_build_code_on_the_host(exe, tmp_path, fx):
+    """Camera.get_bev_maps (surroundBEV.py:105-108) for all four fixture cameras through the code k_warp_maps<1> runs
+    (undistort map evaluated at the taps, FP32 plane interpolation, cvRound + saturate), against cv2.warpPerspective of
+    the cv2-built 2560x2048 map planes; and k_warp_maps<0> on given planes with a random homography."""
+    g = fx.geometry(1280, 1024, 1000, 1000)
+    for name in ("front", "back", "left", "right"):
+        K, D, Hm = fx.calib[name]
+        ref = C.RefCamera(K, D, Hm, g)
+        out = tmp_path / "bev.bin"
+        vals = list(K.ravel()) + list(np.asarray(D, np.float64).ravel()[:4]) + list(ref.P.ravel()) + list(Hm.ravel())
+        _run(exe, ["bevmaps", 2560, 2048, 1000, 1000, out], vals)
+        raw = np.fromfile(out, np.uint8)
+        m1 = raw[:4000000].view(np.int16).reshape(1000, 1000, 2)
+        m2 = raw[4000000:].view(np.uint16).reshape(1000, 1000)
+        assert (m1 == ref.bev_maps[0]).all() and (m2 == ref.bev_maps[1]).all(), name
+    rng = np.random.default_rng(13)
+    p1 = rng.integers(-5, 500, (120, 160, 2)).astype(np.int16)
+    p2 = rng.integers(0, 1024, (120, 160)).astype(np.uint16)
+    Hm = np.eye(3) + rng.normal(0, [[0.2, 0.2, 20], [0.2, 0.2, 20], [5e-4, 5e-4, 0]])
+    with open(tmp_path / "planes.bin", "wb") as f:
+        f.write(p1.tobytes()); f.write(p2.tobytes())
+    _run(exe, ["warpmaps", 160, 120, 140, 90, tmp_path / "planes.bin", tmp_path / "warped.bin"], list(Hm.ravel()))
+    raw = np.fromfile(tmp_path / "warped.bin", np.uint8)
+    n = 140 * 90
+    assert (raw[:4 * n].view(np.int16).reshape(90, 140, 2) == cv2.warpPerspective(p1, Hm, (140, 90))).all()
+    assert (raw[4 * n:].view(np.uint16).reshape(90, 140) == cv2.warpPerspective(p2, Hm, (140, 90))).all()
