@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) k_warp_maps(WarpMapsArgs a) {
 // ---------------------------------------------------------------------------------
 struct BlendArgs { const uint8_t* polys; uint8_t* out; int w, h; int lines[8][4]; };
 
-__device__ __forceinline__ double seg_dist(double px, double py, const int* L) {
+__host__ __device__ __forceinline__ double seg_dist(double px, double py, const int* L) {
   const double ax = L[0], ay = L[1], bx = L[2], by = L[3];
   const double dx = bx - ax, dy = by - ay;
   const double d1x = px - ax, d1y = py - ay, d2x = px - bx, d2y = py - by;
@@ -197,13 +197,11 @@ __device__ __forceinline__ double seg_dist(double px, double py, const int* L) {
     const double cr = dadd(dmul(d1y, dx), -dmul(d1x, dy));
     sq = ddiv(dmul(cr, cr), dadd(dmul(dx, dx), dmul(dy, dy)));
   }
-  return __dsqrt_rn(sq);
+  return dsqrt(sq);
 }
 
-__global__ void __launch_bounds__(256) k_blend_masks(BlendArgs a) {
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= a.w || y >= a.h) return;
+// One canvas pixel of the four blend masks (host-capable for tests/host/kernel_math.cu).
+__host__ __device__ __forceinline__ void blend_pixel(const BlendArgs& a, int x, int y) {
   const size_t plane = (size_t)a.w * a.h, p = (size_t)y * a.w + x;
   uint8_t m[4];
 #pragma unroll
@@ -226,6 +224,13 @@ __global__ void __launch_bounds__(256) k_blend_masks(BlendArgs a) {
     }
     a.out[n * plane + p] = (uint8_t)v;
   }
+}
+
+__global__ void __launch_bounds__(256) k_blend_masks(BlendArgs a) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= a.w || y >= a.h) return;
+  blend_pixel(a, x, y);
 }
 
 // ---------------------------------------------------------------------------------

@@ -165,7 +165,29 @@ static int mode_warpmaps(int sw, int sh, int dw, int dh, const char* in_path, co
   return write_planes(out_path, m1, m2, nd);
 }
 
+//   kernel_math blend <w> <h> <polys.bin> <out.bin>   stdin: lines[8][4]   (BlendMask.get_blend_mask, :270-277, k_blend_masks code)
+static int mode_blend(int w, int h, const char* in_path, const char* out_path) {
+  double L[32];
+  if (!read_doubles(L, 32)) return 2;
+  const size_t n = (size_t)w * h * 4;
+  uint8_t* polys = (uint8_t*)malloc(n);
+  uint8_t* out = (uint8_t*)malloc(n);
+  FILE* f = fopen(in_path, "rb");
+  if (!f || fread(polys, 1, n, f) != n) return 5;
+  fclose(f);
+  BlendArgs a;
+  a.polys = polys; a.out = out; a.w = w; a.h = h;
+  for (int i = 0; i < 8; ++i) for (int j = 0; j < 4; ++j) a.lines[i][j] = (int)L[i * 4 + j];
+  for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) blend_pixel(a, x, y);
+  f = fopen(out_path, "wb");
+  if (!f) return 4;
+  fwrite(out, 1, n, f);
+  fclose(f);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc == 6 && !strcmp(argv[1], "blend")) return mode_blend(atoi(argv[2]), atoi(argv[3]), argv[4], argv[5]);
   if (argc == 7 && !strcmp(argv[1], "bevmaps")) return mode_bevmaps(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argv[6]);
   if (argc == 8 && !strcmp(argv[1], "warpmaps"))
     return mode_warpmaps(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argv[6], argv[7]);

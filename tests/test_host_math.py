@@ -154,3 +154,18 @@ def test_bev_lut_build_code_on_the_host(exe, tmp_path, fx):
     n = 140 * 90
     assert (raw[:4 * n].view(np.int16).reshape(90, 140, 2) == cv2.warpPerspective(p1, Hm, (140, 90))).all()
     assert (raw[4 * n:].view(np.uint16).reshape(90, 140) == cv2.warpPerspective(p2, Hm, (140, 90))).all()
+
+
+def test_blend_weight_code_on_the_host(exe, tmp_path):
+    """BlendMask.get_blend_mask (surroundBEV.py:270-277): the k_blend_masks pixel code on the host against the oracle's
+    restatement (itself pinned to the reference's pointPolygonTest loop in test_oracle.py), two geometries."""
+    names = ("front", "back", "left", "right")
+    for BW, BH, CW, CH in ((1000, 1000, 250, 400), (333, 257, 83, 102)):
+        polys = np.stack([R.fill_poly(BW, BH, R.blend_polygon(n, BW, BH, CW, CH)) for n in names])
+        L = R.blend_lines(BW, BH, CW, CH)
+        lines = np.stack([np.asarray(L[k]).reshape(4) for k in ("FL", "FR", "BL", "BR", "LF", "LB", "RF", "RB")])
+        (tmp_path / "polys.bin").write_bytes(polys.tobytes())
+        _run(exe, ["blend", BW, BH, tmp_path / "polys.bin", tmp_path / "blend.bin"], list(lines.ravel()))
+        got = np.fromfile(tmp_path / "blend.bin", np.uint8).reshape(4, BH, BW)
+        for i, n in enumerate(names):
+            assert (got[i] == R.blend_mask(n, BW, BH, CW, CH)).all(), (n, BW, BH)
