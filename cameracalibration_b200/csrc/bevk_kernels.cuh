@@ -287,36 +287,45 @@ __global__ void __launch_bounds__(256) k_vsum(const uint8_t* const* __restrict__
 }
 
 // K8 part 2: delta_c = cvRound(V_mean - V_c) per frame-set (cv2.add rounds the scalar).
+// luminance offsets of one frame-set from its exact V sums (surroundBEV.py:66-74); host-capable for the CPU tests
+__host__ __device__ __forceinline__ void lum_deltas(const unsigned long long* vsum, int n_cam, double npix, int* delta) {
+  double tot = 0.0;
+  for (int c = 0; c < n_cam; ++c) tot = dadd(tot, ddiv((double)vsum[c], npix));
+  const double vmean = ddiv(tot, (double)n_cam);
+  for (int c = 0; c < n_cam; ++c) delta[c] = cv_round(dadd(vmean, -ddiv((double)vsum[c], npix)));
+}
+
 __global__ void k_delta(const unsigned long long* __restrict__ vsum, int n_cam, int batch, double npix,
                         int* __restrict__ delta) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
-  double tot = 0.0;
-  for (int c = 0; c < n_cam; ++c) tot = dadd(tot, ddiv((double)vsum[b * n_cam + c], npix));
-  const double vmean = ddiv(tot, (double)n_cam);
-  for (int c = 0; c < n_cam; ++c)
-    delta[b * n_cam + c] = cv_round(dadd(vmean, -ddiv((double)vsum[b * n_cam + c], npix)));
+  lum_deltas(vsum + b * n_cam, n_cam, npix, delta + b * n_cam);
 }
 
 // ---------------------------------------------------------------------------------
 // K9: color_balance (surroundBEV.py:43-55) + car overlay.  Gains from the channel sums;
 // out = sat(cvRound(double(px) * K_c)) through a 3x256 table built per CTA in shared memory.
 // ---------------------------------------------------------------------------------
+// grey-world gains of one canvas from its channel sums, and one entry of the 3 x 256 output table (host-capable)
+__host__ __device__ __forceinline__ void gray_world_gains(const unsigned long long* csum, double npix, double* gain) {
+  const double B = ddiv((double)csum[0], npix), G = ddiv((double)csum[1], npix), R = ddiv((double)csum[2], npix);
+  const double K = ddiv(dadd(dadd(R, G), B), 3.0);
+  gain[0] = ddiv(K, B); gain[1] = ddiv(K, G); gain[2] = ddiv(K, R);
+}
+__host__ __device__ __forceinline__ uint8_t gain_entry(double gain, int v) {
+  const int r = cv_round(dmul((double)v, gain));   // non-finite -> INT_MIN -> saturates to 0, as on x86
+  return (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+}
+
 __global__ void __launch_bounds__(256) k_gain(uint8_t* __restrict__ canvas, long long canvas_bytes, double npix,
                                               const unsigned long long* __restrict__ csum,
                                               const uint8_t* __restrict__ car) {
   __shared__ uint8_t tab[3][256];
   const int b = blockIdx.y;
   {
-    const double B = ddiv((double)csum[b * 3 + 0], npix), G = ddiv((double)csum[b * 3 + 1], npix),
-                 R = ddiv((double)csum[b * 3 + 2], npix);
-    const double K = ddiv(dadd(dadd(R, G), B), 3.0);
-    const double gain[3] = {ddiv(K, B), ddiv(K, G), ddiv(K, R)};
-    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
-      const int c = i >> 8, v = i & 255;
-      const int r = cv_round(dmul((double)v, gain[c]));   // non-finite -> INT_MIN -> saturates to 0, as on x86
-      tab[c][v] = (uint8_t)max(0, min(255, r));
-    }
+    double gain[3];
+    gray_world_gains(csum + b * 3, npix, gain);
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) tab[i >> 8][i & 255] = gain_entry(gain[i >> 8], i & 255);
   }
   __syncthreads();
   uint8_t* cv = canvas + (size_t)b * canvas_bytes;

@@ -186,7 +186,27 @@ static int mode_blend(int w, int h, const char* in_path, const char* out_path) {
   return 0;
 }
 
+//   kernel_math balance   stdin: npix_frames npix_canvas  vsum[4]  csum[3]  -> prints 4 luminance offsets and the 3 x 256 gain table
+static int mode_balance() {
+  double v[9];
+  if (!read_doubles(v, 9)) return 2;
+  unsigned long long vsum[4], csum[3];
+  for (int i = 0; i < 4; ++i) vsum[i] = (unsigned long long)v[2 + i];
+  for (int i = 0; i < 3; ++i) csum[i] = (unsigned long long)v[6 + i];
+  int delta[4];
+  lum_deltas(vsum, 4, v[0], delta);
+  printf("%d %d %d %d\n", delta[0], delta[1], delta[2], delta[3]);
+  double gain[3];
+  gray_world_gains(csum, v[1], gain);
+  for (int c = 0; c < 3; ++c) {
+    for (int i = 0; i < 256; ++i) printf("%d ", (int)gain_entry(gain[c], i));
+    printf("\n");
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc == 2 && !strcmp(argv[1], "balance")) return mode_balance();
   if (argc == 6 && !strcmp(argv[1], "blend")) return mode_blend(atoi(argv[2]), atoi(argv[3]), argv[4], argv[5]);
   if (argc == 7 && !strcmp(argv[1], "bevmaps")) return mode_bevmaps(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argv[6]);
   if (argc == 8 && !strcmp(argv[1], "warpmaps"))

@@ -169,3 +169,28 @@ def test_blend_weight_code_on_the_host(exe, tmp_path):
         got = np.fromfile(tmp_path / "blend.bin", np.uint8).reshape(4, BH, BW)
         for i, n in enumerate(names):
             assert (got[i] == R.blend_mask(n, BW, BH, CW, CH)).all(), (n, BW, BH)
+
+
+def test_balance_scalar_code_on_the_host(exe, fx):
+    """luminance_balance's offsets (surroundBEV.py:66-74) and color_balance's gains (:43-55) from exact integer sums:
+    the k_delta / k_gain scalar code on the host against the reference's cv2 call sequence on the fixture frames."""
+    frames = fx.frames()
+    rng = np.random.default_rng(14)
+    canvas = rng.integers(0, 256, (300, 400, 3), dtype=np.uint8)
+    canvas[..., 1] //= 2                                         # distinct channel means -> gains away from 1
+    vsum = [int(f.max(axis=2).astype(np.int64).sum()) for f in frames]
+    csum = [int(canvas[..., c].astype(np.int64).sum()) for c in range(3)]
+    vals = [frames[0].shape[0] * frames[0].shape[1], canvas.shape[0] * canvas.shape[1]] + vsum + csum
+    r = subprocess.run([exe, "balance"], input=" ".join(float(v).hex() for v in vals), capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    rows = r.stdout.strip().split("\n")
+    assert [int(t) for t in rows[0].split()] == R.luminance_offsets(frames)[0] == [6, -1, -6, 0]     # SURVEY 8a-11
+    table = np.array([[int(t) for t in row.split()] for row in rows[1:4]], np.uint8)
+    got = np.stack([table[c][canvas[..., c]] for c in range(3)], axis=-1)
+    assert (got == C.color_balance(canvas.copy())).all()
+    # the offsets are what the reference's float expression rounds to: V += (mean of means - own mean), cv2.add saturating
+    hsv_v = [cv2.split(cv2.cvtColor(f, cv2.COLOR_BGR2HSV))[2] for f in frames]
+    means = [np.mean(v) for v in hsv_v]
+    vm = (means[0] + means[1] + means[2] + means[3]) / 4
+    for v, m, d in zip(hsv_v, means, [int(t) for t in rows[0].split()]):
+        assert (cv2.add(v, (vm - m)) == np.clip(v.astype(np.int32) + d, 0, 255)).all()
