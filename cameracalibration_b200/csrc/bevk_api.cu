@@ -18,10 +18,10 @@
 #include "bevk_kernels.cuh"
 #include "bevk_bev.cuh"
 #include "bevk_gather4.cuh"
+#include "bevk_plan.cuh"
 
 using namespace bevk;
 
-#define BEVK_MAX_BANDS 8
 
 // ------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -542,94 +542,23 @@ int bevk_bev_finalize(bevk_ctx* c) {
     CU(cudaMemcpyAsync(m2[k].data(), c->cam[k].map2.p, npx * 2, cudaMemcpyDeviceToHost, c->stream));
   }
   CU(cudaStreamSynchronize(c->stream));
-  const unsigned pitch = (unsigned)FW * 3u;
-  const long long frame_bytes = (long long)pitch * FH;
-  const int tx = (BW + TILE - 1) / TILE, ty = (BH + TILE - 1) / TILE;
-  std::vector<int4> tiles;
-  std::vector<BevItem> items;
-  std::vector<uint4> lut;
-  tiles.reserve((size_t)tx * ty);
   c->nb_override = 0;
   if (const char* env = getenv("BEVK_NB")) {   // tuning override of the frame-sets per work unit: 1, 4 or 8
     const int v = atoi(env);
     if (v == 1 || v == 4 || v == 8) c->nb_override = v;
   }
-  // per camera and source row: [first, last+1) column any in-frame tap touches (for k_lum_spans)
-  std::vector<int2> spans((size_t)NC * FH, make_int2(INT_MAX, -1));
-  auto touch = [&](int k, int x, int y) {
-    if (x < 0 || y < 0 || x >= FW || y >= FH) return;
-    int2& sp = spans[(size_t)k * FH + y];
-    sp.x = std::min(sp.x, x); sp.y = std::max(sp.y, x + 1);
-  };
-  for (int tj = 0; tj < ty; ++tj)
-    for (int ti = 0; ti < tx; ++ti) {
-      const int x0 = ti * TILE, y0 = tj * TILE;
-      int4 t = make_int4(x0, y0, (int)items.size(), 0);
-      for (int k = 0; k < NC; ++k) {
-        const uint8_t* mk = c->cam[k].mask.data();
-        bool any = false;
-        long long cx = 0, cy = 0;   // source-row changes along canvas x vs canvas y
-        auto in_frame = [&](int sx, int sy) {
-          const long long off = (long long)sy * pitch + (long long)sx * 3;
-          return sx >= 0 && sy >= 0 && sx + 1 < FW && sy + 1 < FH && !(pitch & 3u) && off + pitch + 12 <= frame_bytes;
-        };
-        for (int y = y0; y < std::min(y0 + TILE, BH); ++y)
-          for (int x = x0; x < std::min(x0 + TILE, BW); ++x) {
-            const size_t p = (size_t)y * BW + x;
-            if (!mk[p]) continue;
-            any = true;
-            int sx = m1[k][2 * p], sy = m1[k][2 * p + 1];
-            if (c->bev_interp == BEVK_INTER_NEAREST) {   // same shift as in the entry builder below
-              sx += ((m2[k][p] & 31u) < 16u); sy += (((m2[k][p] >> 5) & 31u) < 16u);
-            }
-            touch(k, sx, sy); touch(k, sx + 1, sy); touch(k, sx, sy + 1); touch(k, sx + 1, sy + 1);
-            if (x + 1 < BW && mk[p + 1]) cx += std::abs(m1[k][2 * (p + 1) + 1] - sy);
-            if (y + 1 < BH && mk[p + BW]) cy += std::abs(m1[k][2 * (p + BW) + 1] - sy);
-          }
-        if (!any) continue;
-        BevItem item{};
-        item.cam = k;
-        item.orient = cy < cx ? 1 : 0;
-        const size_t base = lut.size();
-        lut.resize(base + TILE * TILE, make_uint4(0u, 0u, 0u, 0u));
-        for (int kk = 0; kk < 4; ++kk)
-          for (int th = 0; th < 256; ++th) {
-            const int lane = th & 31, major = (th >> 5) * 4 + kk;
-            const int x = x0 + (item.orient ? major : lane), y = y0 + (item.orient ? lane : major);
-            if (x >= BW || y >= BH) continue;
-            const size_t p = (size_t)y * BW + x;
-            const unsigned w = mk[p];
-            if (!w) continue;
-            int sx = m1[k][2 * p], sy = m1[k][2 * p + 1];
-            unsigned frac = m2[k][p] & 1023u;
-            if (c->bev_interp == BEVK_INTER_NEAREST) {
-              // cv2.remap INTER_NEAREST with fixed-point maps: OpenCV's inverted NNDeltaTab picks the +1
-              // neighbour when the fraction is < 16; a zero fraction then makes the bilinear formula
-              // return exactly that texel ((1024 p + 512) >> 10 == p), so the kernel needs no NN variant
-              sx += ((frac & 31u) < 16u); sy += ((frac >> 5) < 16u);
-              frac = 0;
-            }
-            const unsigned fx = frac & 31u, fy = frac >> 5;
-            const unsigned w11 = fx * fy, w01 = (fx << 5) - w11, w10 = (fy << 5) - w11, w00 = 1024u - (fx << 5) - (fy << 5) + w11;
-            uint4 e;
-            e.y = w00 | (w01 << 16);                       // DP2A weight pairs, top / bottom source row
-            e.z = w10 | (w11 << 16);
-            e.w = (w * 257u + 1u) | (frac << 17) | LUT_ACTIVE;   // blend multiplier (w > 0 here), fraction, flags
-            if (!in_frame(sx, sy)) {
-              // out-of-frame taps, a pitch that is not a multiple of 4, or the very end of the frame:
-              // per-tap checked path
-              e.w |= LUT_BORDER;
-              e.x = (unsigned)(unsigned short)sx | ((unsigned)(unsigned short)sy << 16);
-            } else {
-              e.x = (unsigned)((long long)sy * pitch + (long long)sx * 3);
-            }
-            lut[base + kk * 256 + th] = e;
-          }
-        items.push_back(item);
-        t.w++;
-      }
-      tiles.push_back(t);
-    }
+  BevPlan plan;
+  {
+    std::vector<const short*> p1(NC);
+    std::vector<const unsigned short*> p2(NC);
+    std::vector<const uint8_t*> pm(NC);
+    for (int k = 0; k < NC; ++k) { p1[k] = m1[k].data(); p2[k] = m2[k].data(); pm[k] = c->cam[k].mask.data(); }
+    build_bev_plan(NC, FW, FH, BW, BH, c->bev_interp == BEVK_INTER_NEAREST, p1.data(), p2.data(), pm.data(), plan);
+  }
+  std::vector<int4>& tiles = plan.tiles;
+  std::vector<BevItem>& items = plan.items;
+  std::vector<uint4>& lut = plan.lut;
+  std::vector<int2>& spans = plan.spans;
   c->n_tiles = (long long)tiles.size();
   c->n_items = (long long)items.size();
   RET(c->d_tiles.ensure(tiles.size() * sizeof(int4)));
@@ -640,15 +569,12 @@ int bevk_bev_finalize(bevk_ctx* c) {
     CU(cudaMemcpyAsync(c->d_items.p, items.data(), items.size() * sizeof(BevItem), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_lut.p, lut.data(), lut.size() * sizeof(uint4), cudaMemcpyHostToDevice, c->stream));
   }
-  for (auto& sp : spans) if (sp.y < 0) sp = make_int2(0, 0);
   RET(c->d_spans.ensure(spans.size() * sizeof(int2)));
   CU(cudaMemcpyAsync(c->d_spans.p, spans.data(), spans.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
   c->span_px = 0;
   for (const auto& sp : spans) c->span_px += sp.y - sp.x;
-  // Sampled region per camera as a few horizontal bands, each with its own byte range: the host path
-  // uploads only these rectangles of a frame when the whole frame is not needed (i.e. without BALANCE,
-  // whose V means cover the full frame).  The footprint of a fisheye camera under a BEV mask is
-  // fan-shaped: two bands already cut the plain bounding box from 34 % to 23 % of the frame.
+  // Host-path ingest: page-locked frames are read span by span (k_fetch_spans), pageable ones as a few DMA
+  // rectangles per frame (plan_bands); BALANCE needs whole frames (its V means cover them).
   c->zero_copy_ok = true;
   if (const char* env = getenv("BEVK_ZEROCOPY")) c->zero_copy_ok = atoi(env) != 0;
   c->span_fetch_bytes = 0;
@@ -656,26 +582,7 @@ int bevk_bev_finalize(bevk_ctx* c) {
     if (sp.y > sp.x) c->span_fetch_bytes += std::min<int>(FW * 3, (3 * sp.y + 12 + 15) & ~15) - (std::max(0, 3 * sp.x - 12) & ~15);
   c->n_bands = 2;
   if (const char* env = getenv("BEVK_BANDS")) c->n_bands = std::max(1, std::min(BEVK_MAX_BANDS, atoi(env)));
-  for (int k = 0; k < NC; ++k) {
-    int y0 = FH, y1 = 0;
-    for (int y = 0; y < FH; ++y)
-      if (spans[(size_t)k * FH + y].y > spans[(size_t)k * FH + y].x) { y0 = std::min(y0, y); y1 = std::max(y1, y + 1); }
-    for (int bnd = 0; bnd < c->n_bands; ++bnd) {
-      int* bx = c->cam_box[k][bnd];
-      bx[0] = bx[1] = bx[2] = bx[3] = 0;
-      if (y1 <= y0) continue;
-      const int ya = y0 + (int)((long long)(y1 - y0) * bnd / c->n_bands), yb = y0 + (int)((long long)(y1 - y0) * (bnd + 1) / c->n_bands);
-      int x0 = FW, x1 = 0;
-      for (int y = ya; y < yb; ++y) {
-        const int2 sp = spans[(size_t)k * FH + y];
-        if (sp.y > sp.x) { x0 = std::min(x0, sp.x); x1 = std::max(x1, sp.y); }
-      }
-      if (x1 <= x0 || yb <= ya) continue;
-      // the fast path reads whole aligned words around the taps: widen by 4 px each side (touched, never sampled)
-      x0 = std::max(0, x0 - 4); x1 = std::min(FW, x1 + 4);
-      bx[0] = ya; bx[1] = yb; bx[2] = x0 * 3; bx[3] = x1 * 3;
-    }
-  }
+  for (int k = 0; k < NC; ++k) plan_bands(spans.data() + (size_t)k * FH, FW, FH, c->n_bands, c->cam_box[k]);
   // OpenCV's 8-bit HSV division tables (color_hsv: sdiv_table / hdiv_table180, hsv_shift = 12)
   std::vector<int> tab(512, 0);
   for (int i = 1; i < 256; ++i) {

@@ -56,7 +56,21 @@ struct BevParams {
   int cam_lo, cam_hi;
 };
 
-__device__ __forceinline__ unsigned ldg32(const uint8_t* p) { return __ldg(reinterpret_cast<const unsigned*>(p)); }
+// read-only global loads; the host forms serve tests/host/kernel_math.cu
+__host__ __device__ __forceinline__ unsigned ldg32(const uint8_t* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(reinterpret_cast<const unsigned*>(p));
+#else
+  return *reinterpret_cast<const unsigned*>(p);
+#endif
+}
+__host__ __device__ __forceinline__ int ldg8(const uint8_t* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
 #ifndef BEVK_WRITE_COALESCED
 #define BEVK_WRITE_COALESCED 0
 #endif
@@ -90,7 +104,8 @@ __host__ __device__ __forceinline__ unsigned tile_row_word(const unsigned* acc_r
 // out-of-frame taps (BORDER_CONSTANT 0 per tap; also every entry when the pitch is not a multiple
 // of 4).
 struct SlowGeo { unsigned pitch; int FW, FH; };
-__device__ __noinline__ unsigned sample_slow(const SlowGeo P, const uint8_t* __restrict__ src, unsigned ex, unsigned ew) {
+__host__ __device__ __forceinline__ unsigned sample_slow_core(const SlowGeo P, const uint8_t* __restrict__ src, unsigned ex,
+                                                             unsigned ew) {
   int p[4][3];
   const unsigned wm = ew & 0x1ffffu;
   const int sx = (short)(ex & 0xffffu), sy = (short)(ex >> 16);
@@ -101,7 +116,7 @@ __device__ __noinline__ unsigned sample_slow(const SlowGeo P, const uint8_t* __r
     int c0 = 0, c1 = 0, c2 = 0;
     if (in) {
       const uint8_t* q = src + (size_t)ty * P.pitch + 3 * tx;
-      c0 = __ldg(q); c1 = __ldg(q + 1); c2 = __ldg(q + 2);
+      c0 = ldg8(q); c1 = ldg8(q + 1); c2 = ldg8(q + 2);
     }
     p[t][0] = c0; p[t][1] = c1; p[t][2] = c2;
   }
@@ -111,6 +126,9 @@ __device__ __noinline__ unsigned sample_slow(const SlowGeo P, const uint8_t* __r
   unsigned orr = (unsigned)bilerp_q10(p[0][2], p[1][2], p[2][2], p[3][2], fx, fy);
   ob = (ob * wm) >> 16; og = (og * wm) >> 16; orr = (orr * wm) >> 16;
   return ob | (og << 8) | (orr << 16);
+}
+__device__ __noinline__ unsigned sample_slow(const SlowGeo P, const uint8_t* __restrict__ src, unsigned ex, unsigned ew) {
+  return sample_slow_core(P, src, ex, ew);
 }
 
 // cv2.add of two packed BGR pixels: per-byte saturating add (bytes 0..2; byte 3 stays 0)

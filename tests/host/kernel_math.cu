@@ -13,6 +13,7 @@
 
 #include "../../cameracalibration_b200/csrc/bevk_bev.cuh"
 #include "../../cameracalibration_b200/csrc/bevk_kernels.cuh"
+#include "../../cameracalibration_b200/csrc/bevk_plan.cuh"
 
 using namespace bevk;
 
@@ -205,7 +206,138 @@ static int mode_balance() {
   return 0;
 }
 
+//   kernel_math bev <in.bin> <out.bin>
+// One frame-set through the product's plan compiler (bevk_plan.cuh, the code bevk_bev_finalize runs) and a plain-loop
+// interpreter of that plan that uses the kernels' own per-entry arithmetic (interp_fast, sample_slow_core, sat_add_bgr,
+// hsv_roundtrip, lum_deltas, gray_world_gains / gain_entry).  It mirrors k_bev's work decomposition -- tile, item,
+// entry index -> accumulator position by orientation, first-camera store vs saturating add -- and run_device's
+// BALANCE sequence (V sums, offsets, balanced row spans, gather, channel sums, gains, car), without threads.
+// in.bin : int32 NC FW FH BW BH nearest balance has_car; per camera map1 int16[BH*BW*2], map2 uint16[BH*BW],
+//          mask u8[BH*BW]; NC frames u8[FH*FW*3]; car u8[BH*BW*3] if has_car.   out.bin: canvas u8[BH*BW*3]
+static int mode_bev(const char* in_path, const char* out_path) {
+  FILE* f = fopen(in_path, "rb");
+  if (!f) return 5;
+  int hd[8];
+  if (fread(hd, 4, 8, f) != 8) return 5;
+  const int NC = hd[0], FW = hd[1], FH = hd[2], BW = hd[3], BH = hd[4], nearest = hd[5], balance = hd[6], has_car = hd[7];
+  const size_t npx = (size_t)BW * BH, fbytes = (size_t)FW * FH * 3;
+  std::vector<std::vector<short>> m1(NC, std::vector<short>(npx * 2));
+  std::vector<std::vector<unsigned short>> m2(NC, std::vector<unsigned short>(npx));
+  std::vector<std::vector<uint8_t>> mk(NC, std::vector<uint8_t>(npx)), frames(NC, std::vector<uint8_t>(fbytes));
+  for (int k = 0; k < NC; ++k)
+    if (fread(m1[k].data(), 4, npx, f) != npx || fread(m2[k].data(), 2, npx, f) != npx || fread(mk[k].data(), 1, npx, f) != npx) return 5;
+  for (int k = 0; k < NC; ++k) if (fread(frames[k].data(), 1, fbytes, f) != fbytes) return 5;
+  std::vector<uint8_t> car(has_car ? npx * 3 : 0);
+  if (has_car && fread(car.data(), 1, npx * 3, f) != npx * 3) return 5;
+  fclose(f);
+
+  BevPlan plan;
+  {
+    std::vector<const short*> p1(NC);
+    std::vector<const unsigned short*> p2(NC);
+    std::vector<const uint8_t*> pm(NC);
+    for (int k = 0; k < NC; ++k) { p1[k] = m1[k].data(); p2[k] = m2[k].data(); pm[k] = mk[k].data(); }
+    build_bev_plan(NC, FW, FH, BW, BH, nearest != 0, p1.data(), p2.data(), pm.data(), plan);
+  }
+  // ---- BALANCE, part 1 (k_vsum, k_delta, k_lum_spans): balanced copies hold ONLY the sampled row spans
+  std::vector<std::vector<uint8_t>> bal;
+  if (balance) {
+    int sdiv[256] = {0}, hdiv[256] = {0};
+    for (int i = 1; i < 256; ++i) {
+      sdiv[i] = (int)nearbyint((255 << 12) / (1. * i));
+      hdiv[i] = (int)nearbyint((180 << 12) / (6. * i));
+    }
+    std::vector<unsigned long long> vsum(NC, 0ull);
+    for (int k = 0; k < NC; ++k)
+      for (size_t i = 0; i < (size_t)FW * FH; ++i) {
+        const uint8_t* q = frames[k].data() + 3 * i;
+        vsum[k] += (unsigned)(q[0] > q[1] ? (q[0] > q[2] ? q[0] : q[2]) : (q[1] > q[2] ? q[1] : q[2]));
+      }
+    std::vector<int> delta(NC);
+    lum_deltas(vsum.data(), NC, (double)FW * (double)FH, delta.data());
+    bal.assign(NC, std::vector<uint8_t>(fbytes, 0xA5));          // poison: anything outside the spans must never be sampled
+    const int tail = FW - (FW % 32);
+    for (int k = 0; k < NC; ++k)
+      for (int y = 0; y < FH; ++y) {
+        const int2 sp = plan.spans[(size_t)k * FH + y];
+        for (int x = sp.x; x < sp.y; ++x) {
+          const uint8_t* q = frames[k].data() + ((size_t)y * FW + x) * 3;
+          int b = q[0], g = q[1], r = q[2];
+          hsv_roundtrip(b, g, r, delta[k], x >= tail, sdiv, hdiv);
+          uint8_t* o = bal[k].data() + ((size_t)y * FW + x) * 3;
+          o[0] = (uint8_t)b; o[1] = (uint8_t)g; o[2] = (uint8_t)r;
+        }
+      }
+  }
+  // ---- the gather (k_bev)
+  const SlowGeo geo = {(unsigned)FW * 3u, FW, FH};
+  std::vector<uint8_t> canvas(npx * 3, 0);
+  for (const int4& tile : plan.tiles) {
+    unsigned acc[ACC_WORDS];
+    bool first = true;
+    for (int it = tile.z; it < tile.z + tile.w; ++it) {
+      const BevItem item = plan.items[it];
+      const uint8_t* src = (balance ? bal : frames)[item.cam].data();
+      for (int t = 0; t < 256; ++t) {
+        const int lane = t & 31, wrp = t >> 5;
+        const int pos = item.orient ? lane * ACC_WPITCH + wrp * 4 : (wrp * 4) * ACC_WPITCH + lane;
+        const int step = item.orient ? 1 : ACC_WPITCH;
+        for (int k = 0; k < 4; ++k) {
+          const uint4 e = plan.lut[(size_t)it * (TILE * TILE) + k * 256 + t];
+          unsigned* a = acc + pos + k * step;
+          if (!(e.w & LUT_ACTIVE)) { if (first) *a = 0u; continue; }
+          unsigned v;
+          if (e.w & LUT_BORDER) v = sample_slow_core(geo, src, e.x, e.w);
+          else {
+            const unsigned off_al = e.x & ~3u, sh = (e.x & 3u) * 8u, wm = e.w & 0x1ffffu;
+            const bool third = (sh == 24u);
+            const uint8_t* q0 = src + off_al;
+            const uint8_t* q1 = q0 + geo.pitch;
+            v = interp_fast(sh, e.y, e.z, wm, ldg32(q0), ldg32(q0 + 4), third ? ldg32(q0 + 8) : 0u, ldg32(q1), ldg32(q1 + 4),
+                            third ? ldg32(q1 + 8) : 0u);
+          }
+          *a = first ? v : sat_add_bgr(v, *a);
+        }
+      }
+      first = false;
+    }
+    for (int row = 0; row < TILE; ++row)
+      for (int col = 0; col < TILE; ++col) {
+        const int gx = tile.x + col, gy = tile.y + row;
+        if (gx >= BW || gy >= BH) continue;
+        const unsigned px = first ? 0u : acc[row * ACC_WPITCH + col];
+        uint8_t* o = canvas.data() + ((size_t)gy * BW + gx) * 3;
+        o[0] = px & 255u; o[1] = (px >> 8) & 255u; o[2] = (px >> 16) & 255u;
+      }
+  }
+  // ---- BALANCE, part 2 (channel sums in k_bev<true>, k_gain) and the car overlay
+  if (balance) {
+    unsigned long long csum[3] = {0, 0, 0};
+    for (size_t i = 0; i < npx; ++i) for (int c = 0; c < 3; ++c) csum[c] += canvas[3 * i + c];
+    double gain[3];
+    gray_world_gains(csum, (double)BW * (double)BH, gain);
+    uint8_t tab[3][256];
+    for (int c = 0; c < 3; ++c) for (int v = 0; v < 256; ++v) tab[c][v] = gain_entry(gain[c], v);
+    for (size_t i = 0; i < npx; ++i) for (int c = 0; c < 3; ++c) canvas[3 * i + c] = tab[c][canvas[3 * i + c]];
+  }
+  if (has_car)
+    for (size_t i = 0; i < npx * 3; i += 4) {
+      unsigned a = 0, b = 0;
+      const size_t n = npx * 3 - i < 4 ? npx * 3 - i : 4;
+      memcpy(&a, canvas.data() + i, n); memcpy(&b, car.data() + i, n);
+      const unsigned r = lane_addus4(a, b);
+      memcpy(canvas.data() + i, &r, n);
+    }
+  f = fopen(out_path, "wb");
+  if (!f) return 4;
+  fwrite(canvas.data(), 1, npx * 3, f);
+  fclose(f);
+  printf("tiles=%zu items=%zu lut_bytes=%zu\n", plan.tiles.size(), plan.items.size(), plan.lut.size() * sizeof(uint4));
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc == 4 && !strcmp(argv[1], "bev")) return mode_bev(argv[2], argv[3]);
   if (argc == 2 && !strcmp(argv[1], "balance")) return mode_balance();
   if (argc == 6 && !strcmp(argv[1], "blend")) return mode_blend(atoi(argv[2]), atoi(argv[3]), argv[4], argv[5]);
   if (argc == 7 && !strcmp(argv[1], "bevmaps")) return mode_bevmaps(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argv[6]);

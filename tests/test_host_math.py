@@ -194,3 +194,76 @@ def test_balance_scalar_code_on_the_host(exe, fx):
     vm = (means[0] + means[1] + means[2] + means[3]) / 4
     for v, m, d in zip(hsv_v, means, [int(t) for t in rows[0].split()]):
         assert (cv2.add(v, (vm - m)) == np.clip(v.astype(np.int32) + d, 0, 255)).all()
+
+
+# ------------------------------------------------------------------ the whole BEV path on the CPU
+from tests.helpers import NAMES, h16  # noqa: E402
+
+
+def _bev_on_host(exe, tmp_path, fx, g, calib, masks, frames, car, balance, nearest=False):
+    """Product plan compiler + plan interpreter (kernel_math bev): LUT planes built by the host form of the
+    k_warp_maps<1> code, masks as given, one frame-set."""
+    blob = [np.array([4, g.FW, g.FH, g.BW, g.BH, int(nearest), int(balance), int(car is not None)], np.int32).tobytes()]
+    for n, mask in zip(NAMES, masks):
+        K, D, Hm = calib[n]
+        P = C.dst_camera_matrix(K, g.FW, g.FH, g.FS, g.SS)
+        out = tmp_path / "lut.bin"
+        vals = list(np.asarray(K).ravel()) + list(np.asarray(D, np.float64).ravel()[:4]) + list(P.ravel()) + list(np.asarray(Hm).ravel())
+        _run(exe, ["bevmaps", int(g.FW * g.SS), int(g.FH * g.SS), g.BW, g.BH, out], vals)
+        blob += [out.read_bytes(), np.ascontiguousarray(mask, np.uint8).tobytes()]
+    blob += [np.ascontiguousarray(f).tobytes() for f in frames]
+    if car is not None:
+        blob.append(np.ascontiguousarray(car).tobytes())
+    (tmp_path / "bev_in.bin").write_bytes(b"".join(blob))
+    r = subprocess.run([exe, "bev", str(tmp_path / "bev_in.bin"), str(tmp_path / "bev_out.bin")], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    return np.fromfile(tmp_path / "bev_out.bin", np.uint8).reshape(g.BH, g.BW, 3), r.stdout
+
+
+@pytest.mark.parametrize("blend", [False, True])
+@pytest.mark.parametrize("balance", [False, True])
+def test_bev_path_on_the_host_native_golden(exe, tmp_path, fx, blend, balance):
+    """BevGenerator.__call__ (surroundBEV.py:312-325) at the reference's native geometry, all four flag combinations,
+    with and without the car: plan compiler + per-entry kernel arithmetic on the CPU == golden hashes of the reference."""
+    g = fx.geometry()
+    masks = [R.blend_mask(n, g.BW, g.BH, g.CW, g.CH) if blend else C.plain_mask(n, g) for n in NAMES]
+    gold = fx.gold["native"][f"blend{int(blend)}_balance{int(balance)}"]
+    for car_key, car in (("car", fx.car()), ("nocar", None)):
+        out, info = _bev_on_host(exe, tmp_path, fx, g, fx.calib, masks, fx.frames(), car, balance)
+        assert h16(out) == gold[car_key], (car_key, info)
+
+
+@pytest.mark.parametrize("key,FW,FH,BW,BH,blend,balance,car", [
+    ("cfg2_1280x960_1000_plain", 1280, 960, 1000, 1000, False, False, False),
+    ("cfg3_1920x1080_1200_blend_balance_car", 1920, 1080, 1200, 1200, True, True, True),
+    ("odd_1000x750_777x900_blend_balance_car", 1000, 750, 777, 900, True, True, True),
+])
+def test_bev_path_on_the_host_config_golden(exe, tmp_path, fx, key, FW, FH, BW, BH, blend, balance, car):
+    """BASELINE config shapes and an odd geometry (ragged edge tiles, row pitch 3000 = 8 mod 16, 777-px canvas rows)."""
+    g = fx.geometry(FW, FH, BW, BH)
+    masks = [R.blend_mask(n, g.BW, g.BH, g.CW, g.CH) if blend else C.plain_mask(n, g) for n in NAMES]
+    out, _ = _bev_on_host(exe, tmp_path, fx, g, fx.scaled_calib(g), masks, fx.frames(FW, FH), fx.car(BW, BH) if car else None, balance)
+    assert h16(out) == fx.gold["cfg"][key]
+
+
+def test_bev_path_on_the_host_unaligned_pitch_and_nearest(exe, tmp_path, fx):
+    """A frame width whose row pitch is not a multiple of 4 sends every entry through the per-tap checked path
+    (sample_slow_core); INTER_NEAREST is compiled into the plan.  Both against the cv2 call sequence."""
+    g = fx.geometry(333, 250, 203, 177)
+    calib = fx.scaled_calib(g)
+    masks = [R.blend_mask(n, g.BW, g.BH, g.CW, g.CH) for n in NAMES]
+    frames, car = fx.frames(333, 250), fx.car(203, 177)
+    ref = C.RefBev(calib, g, True, True, masks=masks)
+    out, _ = _bev_on_host(exe, tmp_path, fx, g, calib, masks, frames, car, True)
+    assert (out == ref(*frames, car)).all()
+    g2 = fx.geometry(640, 512, 500, 500)
+    calib2 = fx.scaled_calib(g2)
+    masks2 = [C.plain_mask(n, g2) for n in NAMES]
+    frames2 = fx.frames(640, 512)
+    cams = [C.RefCamera(*calib2[n], g2) for n in NAMES]
+    want = np.zeros((500, 500, 3), np.uint8)
+    for cam, m, f in zip(cams, masks2, frames2):
+        want = cv2.add(want, R.apply_plain(cv2.remap(f, *cam.bev_maps, interpolation=cv2.INTER_NEAREST), m))
+    out2, _ = _bev_on_host(exe, tmp_path, fx, g2, calib2, masks2, frames2, None, False, nearest=True)
+    assert (out2 == want).all()
