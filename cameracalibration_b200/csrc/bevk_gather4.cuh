@@ -12,7 +12,7 @@
 namespace bevk {
 
 // one output pixel: fixed-point source position -> packed B | G<<8 | R<<16
-__device__ __forceinline__ unsigned gather_px(const uint8_t* __restrict__ src, unsigned spitch, int sw, int sh, int sx, int sy,
+__host__ __device__ __forceinline__ unsigned gather_px(const uint8_t* __restrict__ src, unsigned spitch, int sw, int sh, int sx, int sy,
                                               unsigned fx, unsigned fy) {
   const bool inside = sx >= 0 && sy >= 0 && sx + 1 < sw && sy + 1 < sh;
   if (inside) {
@@ -32,7 +32,7 @@ __device__ __forceinline__ unsigned gather_px(const uint8_t* __restrict__ src, u
     const int tx = sx + (t & 1), ty = sy + (t >> 1);
     if ((unsigned)tx < (unsigned)sw && (unsigned)ty < (unsigned)sh) {
       const uint8_t* q = src + (size_t)ty * spitch + 3 * tx;
-      p[t][0] = __ldg(q); p[t][1] = __ldg(q + 1); p[t][2] = __ldg(q + 2);
+      p[t][0] = ldg8(q); p[t][1] = ldg8(q + 1); p[t][2] = ldg8(q + 2);
     } else { p[t][0] = p[t][1] = p[t][2] = 0; }
   }
   const unsigned ob = (unsigned)bilerp_q10(p[0][0], p[1][0], p[2][0], p[3][0], (int)fx, (int)fy);

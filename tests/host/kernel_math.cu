@@ -14,6 +14,7 @@
 #include "../../cameracalibration_b200/csrc/bevk_bev.cuh"
 #include "../../cameracalibration_b200/csrc/bevk_kernels.cuh"
 #include "../../cameracalibration_b200/csrc/bevk_plan.cuh"
+#include "../../cameracalibration_b200/csrc/bevk_gather4.cuh"
 
 using namespace bevk;
 
@@ -336,7 +337,61 @@ static int mode_bev(const char* in_path, const char* out_path) {
   return 0;
 }
 
+//   kernel_math gather <mode> <sw> <sh> <dw> <dh> <src.bin> <out.bin>   3-channel INTER_LINEAR through gather_px
+//       mode 1: stdin K[9] D[5] P[9] + model  -> fused undistort (k_gather4<1>: camera model evaluated per pixel)
+//       mode 2: stdin H[9]                    -> cv2.warpPerspective (k_gather4<2>)
+static int mode_gather(int mode, int sw, int sh, int dw, int dh, const char* in_path, const char* out_path) {
+  CamModel cm;
+  Homog hm;
+  memset(&cm, 0, sizeof cm);
+  if (mode == 1) {
+    double K[9], D[5], P[9], model;
+    if (!read_doubles(K, 9) || !read_doubles(D, 5) || !read_doubles(P, 9) || !read_doubles(&model, 1)) return 2;
+    if (!inv3(P, cm.iR)) return 3;
+    for (int i = 0; i < 5; ++i) cm.k[i] = D[i];
+    cm.fx = K[0]; cm.fy = K[4]; cm.cx = K[2]; cm.cy = K[5];
+    cm.model = (int)model; cm.w = dw; cm.h = dh;
+  } else {
+    double H[9];
+    if (!read_doubles(H, 9)) return 2;
+    if (!inv3(H, hm.M)) memset(hm.M, 0, sizeof hm.M);
+  }
+  const size_t sbytes = (size_t)sw * sh * 3;
+  std::vector<uint8_t> src(sbytes + 16, 0), dst((size_t)dw * dh * 3);   // slack: the library's buffers have it too
+  FILE* f = fopen(in_path, "rb");
+  if (!f || fread(src.data(), 1, sbytes, f) != sbytes) return 5;
+  fclose(f);
+  for (int y = 0; y < dh; ++y)
+    for (int x = 0; x < dw; ++x) {
+      int sx, sy;
+      unsigned fx, fy;
+      if (mode == 2) {
+        int X, Y;
+        warp_point(hm, x, y, (double)TAB, X, Y);
+        sx = sat_i16(X >> INTER_BITS); sy = sat_i16(Y >> INTER_BITS);
+        fx = X & (TAB - 1); fy = Y & (TAB - 1);
+      } else {
+        double u, v;
+        short mx, my;
+        unsigned short fr;
+        undistort_point(cm, x, y, u, v);
+        quantise_uv(u, v, mx, my, fr, pack_saturates(cm.model, x, cm.w));
+        sx = mx; sy = my; fx = fr & (TAB - 1); fy = (fr >> INTER_BITS) & (TAB - 1);
+      }
+      const unsigned px = gather_px(src.data(), (unsigned)sw * 3u, sw, sh, sx, sy, fx, fy);
+      uint8_t* o = dst.data() + ((size_t)y * dw + x) * 3;
+      o[0] = px & 255u; o[1] = (px >> 8) & 255u; o[2] = (px >> 16) & 255u;
+    }
+  f = fopen(out_path, "wb");
+  if (!f) return 4;
+  fwrite(dst.data(), 1, dst.size(), f);
+  fclose(f);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc == 9 && !strcmp(argv[1], "gather"))
+    return mode_gather(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argv[7], argv[8]);
   if (argc == 4 && !strcmp(argv[1], "bev")) return mode_bev(argv[2], argv[3]);
   if (argc == 2 && !strcmp(argv[1], "balance")) return mode_balance();
   if (argc == 6 && !strcmp(argv[1], "blend")) return mode_blend(atoi(argv[2]), atoi(argv[3]), argv[4], argv[5]);

@@ -267,3 +267,39 @@ def test_bev_path_on_the_host_unaligned_pitch_and_nearest(exe, tmp_path, fx):
         want = cv2.add(want, R.apply_plain(cv2.remap(f, *cam.bev_maps, interpolation=cv2.INTER_NEAREST), m))
     out2, _ = _bev_on_host(exe, tmp_path, fx, g2, calib2, masks2, frames2, None, False, nearest=True)
     assert (out2 == want).all()
+
+
+def test_stand_alone_gathers_on_the_host(exe, tmp_path, fx):
+    """Tools/undistort.py / InCalibrator.undistort (fused form: camera model per pixel) and ExCalibrator.warp through
+    the k_gather4 pixel code (gather_px) on the CPU, against the golden hashes of the reference."""
+    K, D, _ = fx.calib["front"]
+    d5 = list(np.asarray(D, np.float64).ravel()[:4]) + [0.0]
+    front = fx.img("front")
+    (tmp_path / "src.bin").write_bytes(front.tobytes())
+    P = C.dst_camera_matrix(K, 1280, 1024, 1, 1)                                   # Tools/undistort.py defaults
+    _run(exe, ["gather", 1, 1280, 1024, 1280, 1024, tmp_path / "src.bin", tmp_path / "und.bin"],
+         list(K.ravel()) + d5 + list(P.ravel()) + [0.0])
+    und = np.fromfile(tmp_path / "und.bin", np.uint8).reshape(1024, 1280, 3)
+    assert h16(und) == fx.gold["tools_undistort_front"]
+    raw0 = fx.img("raw0")
+    (tmp_path / "src.bin").write_bytes(raw0.tobytes())
+    P = C.dst_camera_matrix(K, 1280, 1024, 0.5, 1)                                 # InCalibrator: FOCAL_SCALE 0.5
+    _run(exe, ["gather", 1, 1280, 1024, 1280, 1024, tmp_path / "src.bin", tmp_path / "und.bin"],
+         list(K.ravel()) + d5 + list(P.ravel()) + [0.0])
+    assert h16(np.fromfile(tmp_path / "und.bin", np.uint8).reshape(1024, 1280, 3)) == fx.gold["incalib_fisheye_raw0"]["undistort"]
+    K2 = np.diag([0.5, 480 / 1024, 1.0]) @ K                                       # BASELINE cfg1b: 640x480
+    small = cv2.resize(raw0, (640, 480), interpolation=cv2.INTER_LINEAR)
+    (tmp_path / "src.bin").write_bytes(small.tobytes())
+    _run(exe, ["gather", 1, 640, 480, 640, 480, tmp_path / "src.bin", tmp_path / "und.bin"],
+         list(K2.ravel()) + d5 + list(C.dst_camera_matrix(K2, 640, 480, 0.5, 1).ravel()) + [0.0])
+    assert h16(np.fromfile(tmp_path / "und.bin", np.uint8).reshape(480, 640, 3)) == fx.gold["incalib_fisheye_raw0_640x480"]["undistort"]
+    Kn = K * np.array([[2.0], [2.0], [1.0]])                                        # InCalibrator('normal'): pinhole model
+    (tmp_path / "src.bin").write_bytes(raw0.tobytes())
+    _run(exe, ["gather", 1, 1280, 1024, 1280, 1024, tmp_path / "src.bin", tmp_path / "und.bin"],
+         list(Kn.ravel()) + list(np.asarray(fx.D5, np.float64).ravel()) + list(C.dst_camera_matrix(Kn, 1280, 1024, 0.5, 1).ravel()) + [1.0])
+    assert h16(np.fromfile(tmp_path / "und.bin", np.uint8).reshape(1024, 1280, 3)) == fx.gold["incalib_normal_raw0"]["undistort"]
+    src = fx.img("src_back")
+    Hm = fx.calib["back"][2]
+    (tmp_path / "src.bin").write_bytes(src.tobytes())
+    _run(exe, ["gather", 2, src.shape[1], src.shape[0], 1000, 1000, tmp_path / "src.bin", tmp_path / "warp.bin"], list(Hm.ravel()))
+    assert h16(np.fromfile(tmp_path / "warp.bin", np.uint8).reshape(1000, 1000, 3)) == fx.gold["excalib_warp_back"]
