@@ -203,9 +203,9 @@ from tests.helpers import NAMES, h16  # noqa: E402
 def _bev_on_host(exe, tmp_path, fx, g, calib, masks, frames, car, balance, nearest=False):
     """Product plan compiler + plan interpreter (kernel_math bev): LUT planes built by the host form of the
     k_warp_maps<1> code, masks as given, one frame-set."""
-    blob = [np.array([4, g.FW, g.FH, g.BW, g.BH, int(nearest), int(balance), int(car is not None)], np.int32).tobytes()]
-    for n, mask in zip(NAMES, masks):
-        K, D, Hm = calib[n]
+    cams = [calib[n] for n in NAMES] if isinstance(calib, dict) else list(calib)
+    blob = [np.array([len(cams), g.FW, g.FH, g.BW, g.BH, int(nearest), int(balance), int(car is not None)], np.int32).tobytes()]
+    for (K, D, Hm), mask in zip(cams, masks):
         P = C.dst_camera_matrix(K, g.FW, g.FH, g.FS, g.SS)
         out = tmp_path / "lut.bin"
         vals = list(np.asarray(K).ravel()) + list(np.asarray(D, np.float64).ravel()[:4]) + list(P.ravel()) + list(np.asarray(Hm).ravel())
@@ -303,3 +303,27 @@ def test_stand_alone_gathers_on_the_host(exe, tmp_path, fx):
     (tmp_path / "src.bin").write_bytes(src.tobytes())
     _run(exe, ["gather", 2, src.shape[1], src.shape[0], 1000, 1000, tmp_path / "src.bin", tmp_path / "warp.bin"], list(Hm.ravel()))
     assert h16(np.fromfile(tmp_path / "warp.bin", np.uint8).reshape(1000, 1000, 3)) == fx.gold["excalib_warp_back"]
+
+
+def test_bev_path_on_the_host_eight_cameras(exe, tmp_path, fx):
+    """BASELINE configs[4] semantics at a small size: 8 cameras, 8 angular wedge masks; oracle = the
+    reference's Camera.raw2bev per camera + the N-way saturating compose."""
+    g = fx.geometry(640, 512, 480, 480)
+    calib4 = fx.scaled_calib(g)
+    c, s_ = np.cos(np.pi / 4), np.sin(np.pi / 4)
+    cx, cy = g.BW / 2, g.BH / 2
+    Rot = np.array([[c, -s_, cx - c * cx + s_ * cy], [s_, c, cy - s_ * cx - c * cy], [0, 0, 1.0]])
+    cams = [calib4[n] for n in NAMES] + [(calib4[n][0], calib4[n][1], Rot @ calib4[n][2]) for n in NAMES]
+    ang = np.linspace(0, 2 * np.pi, 9)
+    masks = []
+    for i in range(8):
+        tri = np.array([[cx, cy], [cx + g.BW * np.cos(ang[i]), cy + g.BW * np.sin(ang[i])],
+                        [cx + g.BW * np.cos(ang[i + 1]), cy + g.BW * np.sin(ang[i + 1])]]).astype(np.int32)
+        masks.append(cv2.fillPoly(np.zeros((g.BH, g.BW), np.uint8), [tri], 255))
+    frames = fx.frames(g.FW, g.FH)
+    frames8 = frames + [np.ascontiguousarray(f[:, ::-1]) for f in frames]
+    want = np.zeros((g.BH, g.BW, 3), np.uint8)
+    for (K, D, Hm), m, f in zip(cams, masks, frames8):
+        want = R.sat_add(want, R.apply_plain(C.RefCamera(K, D, Hm, g).raw2bev(f), m))
+    out, info = _bev_on_host(exe, tmp_path, fx, g, cams, masks, frames8, None, False)
+    assert (out == want).all(), info
