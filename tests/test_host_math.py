@@ -327,3 +327,27 @@ def test_bev_path_on_the_host_eight_cameras(exe, tmp_path, fx):
         want = R.sat_add(want, R.apply_plain(C.RefCamera(K, D, Hm, g).raw2bev(f), m))
     out, info = _bev_on_host(exe, tmp_path, fx, g, cams, masks, frames8, None, False)
     assert (out == want).all(), info
+
+
+def test_plan_compiler_memory_safety_under_sanitizers(tmp_path, fx, exe):
+    """The plan compiler and the interpreter again, built with AddressSanitizer + UBSan, on the geometry with ragged
+    edge tiles and an unaligned pitch: no out-of-bounds plan index, same canvas as the plain build."""
+    nvcc = next((c for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc") if c and os.path.exists(c)), None)
+    san = tmp_path / "kernel_math_san"
+    build = subprocess.run([nvcc, "-O1", "-g", "-std=c++17", "--fmad=false", "-Xcompiler",
+                            "-ffp-contract=off,-fsanitize=address,-fsanitize=undefined,-fno-sanitize-recover=undefined,-fno-omit-frame-pointer",
+                            "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(san),
+                            os.path.join(ROOT, "tests", "host", "kernel_math.cu"), "-lasan", "-lubsan"],
+                           capture_output=True, text=True, timeout=900)
+    if build.returncode != 0:
+        pytest.skip("sanitizer runtime not available: " + build.stderr[-200:])
+    g = fx.geometry(333, 250, 203, 177)
+    calib = fx.scaled_calib(g)
+    masks = [R.blend_mask(n, g.BW, g.BH, g.CW, g.CH) for n in NAMES]
+    frames, car = fx.frames(333, 250), fx.car(203, 177)
+    want, _ = _bev_on_host(exe, tmp_path, fx, g, calib, masks, frames, car, True)
+    env = dict(os.environ, ASAN_OPTIONS="protect_shadow_gap=0:detect_leaks=0")
+    r = subprocess.run([str(san), "bev", str(tmp_path / "bev_in.bin"), str(tmp_path / "bev_san.bin")], capture_output=True, text=True,
+                       timeout=900, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert (np.fromfile(tmp_path / "bev_san.bin", np.uint8).reshape(g.BH, g.BW, 3) == want).all()
