@@ -329,6 +329,51 @@ def test_bev_path_on_the_host_eight_cameras(exe, tmp_path, fx):
     assert (out == want).all(), info
 
 
+def _fuzz_case(rng, case):
+    """Random geometry, maps (sometimes at the int16 extremes), masks and frames -> (input blob, cv2-based expectation)."""
+    NC = int(rng.integers(1, 4))
+    FW, FH = int(rng.integers(8, 90)), int(rng.integers(8, 70))
+    BW, BH = int(rng.integers(5, 80)), int(rng.integers(5, 75))
+    nearest = bool(case % 3 == 2)
+    blob = [np.array([NC, FW, FH, BW, BH, int(nearest), 0, 0], np.int32).tobytes()]
+    frames, maps, masks = [], [], []
+    for _ in range(NC):
+        lo, hi = (-6, 6) if case % 4 else (-40000, 40000)
+        m1 = np.stack([rng.integers(lo, FW + hi, (BH, BW)), rng.integers(lo, FH + hi, (BH, BW))], -1).clip(-32768, 32767).astype(np.int16)
+        m2 = rng.integers(0, 1024, (BH, BW)).astype(np.uint16)
+        kind = rng.integers(0, 3)
+        mask = (rng.integers(0, 2, (BH, BW)) * 255 if kind == 0 else rng.integers(0, 256, (BH, BW)) if kind == 1
+                else np.full((BH, BW), 255)).astype(np.uint8)
+        maps.append((m1, m2)); masks.append(mask)
+        frames.append(rng.integers(0, 256, (FH, FW, 3), dtype=np.uint8))
+        blob += [m1.tobytes(), m2.tobytes(), mask.tobytes()]
+    blob += [f.tobytes() for f in frames]
+    want = np.zeros((BH, BW, 3), np.uint8)
+    for f, (m1, m2), mask in zip(frames, maps, masks):
+        warped = cv2.remap(f, m1, m2, cv2.INTER_NEAREST if nearest else cv2.INTER_LINEAR)
+        want = cv2.add(want, R.apply_blend(warped, mask))
+    return b"".join(blob), want
+
+
+def _run_fuzz(exe_path, tmp_path, n_cases, env=None):
+    rng = np.random.default_rng(500)
+    for case in range(n_cases):
+        blob, want = _fuzz_case(rng, case)
+        (tmp_path / "fz_in.bin").write_bytes(blob)
+        r = subprocess.run([str(exe_path), "bev", str(tmp_path / "fz_in.bin"), str(tmp_path / "fz_out.bin")], capture_output=True,
+                           text=True, timeout=300, env=env)
+        assert r.returncode == 0, (case, r.stderr[-2000:])
+        got = np.fromfile(tmp_path / "fz_out.bin", np.uint8).reshape(want.shape)
+        assert (got == want).all(), (case, want.shape)
+
+
+def test_plan_compiler_fuzz_arbitrary_maps(exe, tmp_path):
+    """bevk_bev_set_maps accepts any CV_16SC2 + CV_16UC1 planes: random maps with taps far outside the frame, random
+    masks (0, 255 and weights), 1-3 cameras, tiny ragged geometries, every pitch alignment, both interpolations --
+    plan compiler + interpreter against cv2.remap + the mask / compose restatement."""
+    _run_fuzz(exe, tmp_path, 48)
+
+
 def test_plan_compiler_memory_safety_under_sanitizers(tmp_path, fx, exe):
     """The plan compiler and the interpreter again, built with AddressSanitizer + UBSan, on the geometry with ragged
     edge tiles and an unaligned pitch: no out-of-bounds plan index, same canvas as the plain build."""
@@ -351,3 +396,4 @@ def test_plan_compiler_memory_safety_under_sanitizers(tmp_path, fx, exe):
                        timeout=900, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     assert (np.fromfile(tmp_path / "bev_san.bin", np.uint8).reshape(g.BH, g.BW, 3) == want).all()
+    _run_fuzz(san, tmp_path, 16, env=env)      # arbitrary maps (int16 extremes included) under the sanitizers too
