@@ -47,7 +47,10 @@ def main():
                f"device-resident ({b['ms_per_step']:.3f} ms per step, roofline {b['roofline']['frac']:.2f} of the measured HBM copy peak), "
                f"{b['e2e']['value'] / 1e3:.1f} k frame-sets/s end-to-end from page-locked host memory "
                f"({b['e2e']['h2d_bytes_per_step'] / 1e6:.0f} MB in + {b['e2e']['d2h_bytes_per_step'] / 1e6:.0f} MB out per step over PCIe), "
-               f"reference cv2 path {ref['value']:.0f} frame-sets/s on the same host (`--impl reference`). "
+               f"reference cv2 path {ref['value']:.0f} frame-sets/s on the same host (`--impl reference`"
+               + (f"; {ref['cpu_frame_set_parallel']['value']:.0f} frame-sets/s when {ref['cpu_frame_set_parallel']['threads']} host threads "
+                  "each run the reference's serial sequence on their own frame-set, reported as `cpu_frame_set_parallel`"
+                  if "cpu_frame_set_parallel" in ref else "") + "). "
                "2 / 4 / 8 GPUs (frame-set sharding, no collective): 433 k / 838 k / 1 675 k device-resident; 8 GPUs end-to-end 37.7 k (host PCIe shared).\n"]
     open(p, "w").write(s + "\n".join(md))
 
