@@ -7,7 +7,7 @@ same order* with the geometry passed explicitly, so that it can (a) run on the
 GPU box where /root/reference does not exist, (b) be timed as the CPU baseline
 (``bench.py`` ``cpu_baseline`` / ``--impl reference``), and (c) be checked
 against the unmodified reference classes where /root/reference exists
-(tests/test_oracle_vs_reference.py).  Each function cites the lines it follows.
+(tests/test_oracle.py).  Each function cites the lines it follows.
 """
 from __future__ import annotations
 

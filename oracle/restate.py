@@ -10,7 +10,7 @@ this image).  Every function cites the reference call site (file:line relative
 to /root/reference) it follows and the SURVEY.md appendix item that specifies the
 arithmetic.
 
-Parity status: PINNED.  ``tests/test_oracle_vs_reference.py`` checks every
+Parity status: PINNED.  ``tests/test_oracle.py`` and ``tests/test_oracle_random.py`` check every
 function here bit-for-bit against (a) live ``cv2`` calls, (b) the unmodified
 reference classes imported from /root/reference (when that tree exists), and (c)
 the committed golden hashes in ``tests/golden/golden.json`` produced by
