@@ -162,9 +162,13 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
+cpu_parallel = None   # set by cpu_reference: the same call sequence, one frame-set per host thread
+
+
 def cpu_reference(w, calib, masks, n_sets, repeats, seconds_cap):
     """The reference's CPU path (its cv2 call sequence, oracle/cv2_path.py) on the same
     workload shape; returns (frame-sets/s, threads, description)."""
+    global cpu_parallel
     import cv2
     from oracle import cv2_path as C
     g = C.Geometry(FW=w["FW"], FH=w["FH"], BW=w["BW"], BH=w["BH"],
@@ -189,6 +193,7 @@ def cpu_reference(w, calib, masks, n_sets, repeats, seconds_cap):
             best = (n / dt, threads, f"{n} frame-sets ({n_sets} distinct) of the workload in {dt:.1f} s, cv2 {cv2.__version__}, "
                                      f"best of cv2 thread counts {{default {default_threads}, all {os.cpu_count()}}}")
     cv2.setNumThreads(default_threads)
+    cpu_parallel = cpu_frame_set_parallel(ref, list(sets), seconds_cap=min(5.0, seconds_cap / 3))
     return best
 
 
@@ -241,6 +246,7 @@ def main():
                           f"blend={w['blend']} balance={w['balance']} (BASELINE {a.workload} shape)",
               "sharding": ("frame-sets per GPU, no data-path collective" if a.shard == "frames" else
                            "cameras per GPU, one NCCL all-gather of partial canvases per step + local saturating-sum compose"),
+              "launch": "one step captured as a CUDA graph, the K timed steps replayed by one bevk_graph_launch call",
               "l2": f"inputs ({w['batch'] * 4 * w['FW'] * w['FH'] * 3 / 1e6:.0f} MB/step) larger than L2; "
                     "the frame-invariant LUT stays L2-resident by design"}
 
@@ -285,6 +291,7 @@ def main():
                                            f"sequence (oracle/cv2_path.py), cv2 {cv2.__version__}, os.cpu_count()={os.cpu_count()}"},
                 "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         line["cpu_frame_set_parallel"] = cpu_frame_set_parallel(ref, sets)
+        line["cpu_baseline"]["frame_set_parallel"] = line["cpu_frame_set_parallel"]
         print(json.dumps(line))
         return 0
 
@@ -292,6 +299,13 @@ def main():
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    # bind this rank to the CPUs (and, by first touch, the memory) of its GPU's NUMA node before anything is allocated
+    from cameracalibration_b200 import hostpin
+    try:
+        cpus = hostpin.pin_to_gpu(local)
+    except Exception as e:   # placement is an optimisation, never a reason to fail
+        cpus = sorted(os.sched_getaffinity(0))
+        print(f"[bench] NUMA pinning skipped: {e}", file=sys.stderr)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -311,9 +325,15 @@ def main():
     sharded = ShardedBev(eng, a.shard if world > 1 else "frames")
     cams = a.shard == "cameras" and world > 1
 
+    use_table = bool(os.environ.get("BEVK_BENCH_TABLE"))   # A/B switch: frames through a device pointer table (round-1 gather kernel)
+
     def step():
-        with torch.cuda.stream(stream):   # NCCL orders itself against torch's current stream
-            sharded.render(ptrs, nb, d_out, None, balance=w["balance"])
+        if cams or use_table:
+            with torch.cuda.stream(stream):   # NCCL orders itself against torch's current stream
+                sharded.render(ptrs, nb, d_out, None, balance=w["balance"])
+        else:
+            # the batch is one uint8[batch][cam][FH][FW][3] tensor = a frame stack: TMA-staged kernel
+            eng.run_stack(d_frames.data_ptr(), fbytes, nb, d_out.data_ptr(), 0, w["balance"])
 
     def barrier():
         if world > 1:
@@ -325,11 +345,22 @@ def main():
     for _ in range(max(3, a.warmup)):
         step()
     barrier()
+    # One step is captured into a CUDA graph and the K timed steps are K replays enqueued by ONE C call
+    # (bevk_graph_launch): the device never waits for Python, whatever else the host is doing (8 ranks + samplers).
+    graph = None
+    if not cams and not use_table and not os.environ.get("BEVK_BENCH_NO_GRAPH"):
+        with eng.ctx.graph_capture() as graph:
+            step()
+        graph.launch(3)
+        barrier()
     l0 = eng.ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(a.steps):
-        step()
+    if graph is not None:
+        graph.launch(a.steps)
+    else:
+        for _ in range(a.steps):
+            step()
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -353,6 +384,7 @@ def main():
         step()
         kt.append(eng.last_kernel_ms())
     k_ms = float(np.median(kt))
+    path_used = eng.last_path()
 
     # ---- end to end through the public API, pinned host frames ----
     from cameracalibration_b200 import pinned_empty
@@ -378,6 +410,37 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * nb * n_e2e / float(te.item())   # e2e always runs the frames policy (each rank its own batch)
     same = bool((torch.from_numpy(np.asarray(pin_out)).to(dev) == d_out).all().item())
+
+    # ---- the reference's own call: BevGenerator.__call__(front, back, left, right), one frame-set, NumPy in / NumPy out
+    e2e_api = None
+    if rank == 0 and not os.environ.get("BEVK_BENCH_NO_API"):
+        from cameracalibration_b200.SurroundBirdEyeView import surroundBEV as S
+        ar = S.BevGenerator.get_args()
+        saved = {k: getattr(ar, k) for k in ("FRAME_WIDTH", "FRAME_HEIGHT", "BEV_WIDTH", "BEV_HEIGHT", "CAR_WIDTH", "CAR_HEIGHT")}
+        ar.FRAME_WIDTH, ar.FRAME_HEIGHT, ar.BEV_WIDTH, ar.BEV_HEIGHT = w["FW"], w["FH"], w["BW"], w["BH"]
+        ar.CAR_WIDTH, ar.CAR_HEIGHT = g.CW, g.CH
+        try:
+            gen = S.BevGenerator(blend=w["blend"], balance=w["balance"], calib=calib)
+        finally:
+            for k, v in saved.items():
+                setattr(ar, k, v)
+        e2e_api = {"api": "BevGenerator.__call__(front, back, left, right) -> ndarray, ONE frame-set per call, as "
+                          "surroundBEV.py:312-325 is used; result freshly allocated (pageable)", "unit": unit}
+        for kind in ("pageable", "pinned"):
+            if kind == "pageable":
+                fsets = [[np.array(host[b % nb, c_]) for c_ in range(nc)] for b in range(4)]      # what cv2.imread returns
+            else:
+                fsets = [[pin_in[0, b % nb, c_] for c_ in range(nc)] for b in range(4)]
+            for i in range(6):
+                res = gen(*fsets[i & 3])
+            n_api = 60
+            t0 = time.perf_counter()
+            for i in range(n_api):
+                res = gen(*fsets[i & 3])
+            dt_api = time.perf_counter() - t0
+            ok = bool((res == np.asarray(pin_out[(n_api - 1) & 3 if nb > 3 else 0])).all()) if not w["balance"] else None
+            e2e_api[kind] = {"value": n_api / dt_api, "ms_per_call": dt_api / n_api * 1e3, "matches_batched_path": ok}
+        e2e_api["value"] = e2e_api["pageable"]["value"]
     _, d2h_set = eng.host_copy_bytes(w["balance"])
     h2d_set = eng.last_h2d_bytes() // nb                    # bytes the last bevk_bev_run call actually moved, per frame-set
 
@@ -407,17 +470,20 @@ def main():
                         "d2h_bytes_per_step": nb * d2h_set, "steps": n_e2e, "frame_bytes_per_step": nb * nc * fbytes,
                         "api": "BevEngine.run (ctypes -> bevk_bev_run), pinned host frames; without balance only the "
                                "row spans of each frame its camera's LUT can sample cross PCIe (k_fetch_spans)", "matches_device_path": same},
+                "e2e_api": e2e_api,
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "kernel": "k_bev<false,4>", "kernel_ms": launch_ms,
+                             "traffic": traffic, "kernel": "k_bev_tma<false,4>" if eng.last_path() == "tma" else "k_bev<false,4>",
+                             "kernel_ms": launch_ms,
                              "kernel_ms_isolated": k_ms, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg,
                              "algorithmic_bytes_per_frame_set": {"source_unique_32B_sectors": src_b, "canvas_write": canvas_b}},
-                "clocks": sampler.summary(), "plan": eng.plan_info()}
+                "clocks": sampler.summary(), "plan": dict(eng.plan_info(), tma=eng.tma_plan_info(), path=path_used)}
         if not a.no_cpu_baseline and world == 1:
             v, cores, sample = cpu_reference(w, calib, masks, n_sets=4, repeats=100000, seconds_cap=20.0)
             line["cpu_baseline"] = {"value": v, "unit": unit, "cores": cores, "kind": "port",
-                                    "sample": sample + f"; os.cpu_count()={os.cpu_count()}"}
+                                    "sample": sample + f"; os.cpu_count()={os.cpu_count()}",
+                                    "frame_set_parallel": cpu_parallel}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

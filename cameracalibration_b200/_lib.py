@@ -4,6 +4,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -26,13 +27,14 @@ SIGNATURES = {
     "bevk_ctx_destroy": (C.c_int, [_p]),
     "bevk_ctx_set_stream": (C.c_int, [_p, _p]),
     "bevk_ctx_sync": (C.c_int, [_p]),
+    "bevk_device_pci_bus_id": (C.c_int, [C.c_int, C.c_char_p, C.c_int]),
     "bevk_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(_p)]),
     "bevk_host_free": (C.c_int, [_p]),
     "bevk_undistort_map": (C.c_int, [_p, C.c_int, _dp, _dp, C.c_int, _dp, C.c_int, C.c_int, _p, _p]),
     "bevk_remap": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int64, C.c_int, _p, _p, C.c_int, C.c_int, _p, C.c_int64, C.c_int]),
     "bevk_undistorter_set": (C.c_int, [_p, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int]),
     "bevk_undistorter_maps": (C.c_int, [_p, C.c_int, _p, _p]),
-    "bevk_undistort": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_int, C.c_int64, C.c_int, _p, C.c_int64, C.c_int]),
+    "bevk_undistort": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_int, C.c_int64, C.c_int, _p, C.c_int, C.c_int, C.c_int64, C.c_int]),
     "bevk_warp_perspective": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int64, C.c_int, _dp, _p, C.c_int, C.c_int, C.c_int64, C.c_int]),
     "bevk_warp_maps": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, _dp, C.c_int, C.c_int, _p, _p]),
     "bevk_bev_configure": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -46,7 +48,9 @@ SIGNATURES = {
     "bevk_bev_run": (C.c_int, [_p, C.POINTER(_p), C.c_int64, C.c_int, _p, C.c_int, _p]),
     "bevk_bev_run_device": (C.c_int, [_p, _p, C.c_int, _p, C.c_int, _p]),
     "bevk_bev_run_frames": (C.c_int, [_p, _p, C.c_int, _p, C.c_int, _p]),
+    "bevk_bev_run_stack": (C.c_int, [_p, _p, C.c_int64, C.c_int, _p, C.c_int, _p]),
     "bevk_bev_run_device_cams": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _p]),
+    "bevk_bev_run_stack_cams": (C.c_int, [_p, _p, C.c_int64, C.c_int, C.c_int, C.c_int, _p]),
     "bevk_sat_sum_device": (C.c_int, [_p, C.POINTER(_p), C.c_int, C.c_uint64, _p, _p]),
     "bevk_apply_mask": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, _p]),
     "bevk_color_balance": (C.c_int, [_p, _p, C.c_int, C.c_int, _p]),
@@ -54,6 +58,12 @@ SIGNATURES = {
     "bevk_bev_plan_info": (C.c_int, [_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bevk_bev_host_copy_bytes": (C.c_int, [_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bevk_bev_last_h2d_bytes": (C.c_int64, [_p]),
+    "bevk_bev_last_path": (C.c_int, [_p]),
+    "bevk_bev_tma_plan_info": (C.c_int, [_p] + [C.POINTER(C.c_int64)] * 5),
+    "bevk_graph_begin": (C.c_int, [_p]),
+    "bevk_graph_end": (C.c_int, [_p, C.POINTER(C.c_int)]),
+    "bevk_graph_launch": (C.c_int, [_p, C.c_int, C.c_int]),
+    "bevk_graph_destroy": (C.c_int, [_p, C.c_int]),
     "bevk_launch_count": (C.c_int64, [_p]),
     "bevk_last_kernel_ms": (C.c_int, [_p, C.POINTER(C.c_float)]),
 }
@@ -149,9 +159,41 @@ class Context:
     def sync(self):
         check(self.lib.bevk_ctx_sync(self.h))
 
+    def graph_capture(self):
+        """``with ctx.graph_capture() as g: <device-pointer calls>`` -> g.launch(times).  The calls inside the block are
+        recorded into a CUDA graph instead of executed (run them once before, so every buffer exists)."""
+        return _GraphCapture(self)
+
     @property
     def launches(self) -> int:
         return int(self.lib.bevk_launch_count(self.h))
+
+
+class _GraphCapture:
+    def __init__(self, ctx: Context):
+        self.ctx, self.id = ctx, None
+
+    def __enter__(self):
+        check(self.ctx.lib.bevk_graph_begin(self.ctx.h))
+        return self
+
+    def __exit__(self, et, ev, tb):
+        gid = C.c_int(-1)
+        rc = self.ctx.lib.bevk_graph_end(self.ctx.h, C.byref(gid))
+        if et is None:
+            check(rc)
+            self.id = gid.value
+        return False
+
+    def launch(self, times: int = 1):
+        if self.id is None:
+            raise BevkError("graph capture did not complete")
+        check(self.ctx.lib.bevk_graph_launch(self.ctx.h, self.id, int(times)))
+
+    def destroy(self):
+        if self.id is not None and getattr(self.ctx, "h", None):
+            check(self.ctx.lib.bevk_graph_destroy(self.ctx.h, self.id))
+            self.id = None
 
 
 _default_ctx: dict[int, Context] = {}
@@ -165,16 +207,21 @@ def default_context(device: int | None = None) -> Context:
     return _default_ctx[device]
 
 
+def _free_pinned(addr: int):
+    try:
+        if _lib is not None:
+            _lib.bevk_host_free(_p(addr))
+    except Exception:
+        pass
+
+
 def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
-    """numpy array backed by page-locked host memory (full-rate PCIe copies)."""
+    """numpy array backed by page-locked host memory (full-rate PCIe copies).  The allocation is returned with
+    bevk_host_free when the array and every view of it have been garbage-collected."""
     lib = load()
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
     p = _p()
     check(lib.bevk_host_alloc(n, C.byref(p)))
     buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    _pinned_keep[arr.ctypes.data] = (buf, p)
-    return arr
-
-
-_pinned_keep: dict = {}
+    weakref.finalize(buf, _free_pinned, p.value)     # numpy keeps `buf` alive as the base of the array and its views
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)

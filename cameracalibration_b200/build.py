@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbevk.so")
 SOURCES = ["bevk_api.cu"]
-DEPS = ["bevk_api.cu", "bevk_kernels.cuh", "bevk_bev.cuh", "bevk_gather4.cuh", "bevk_device.cuh", os.path.join("..", "..", "include", "bevk.h")]
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + [os.path.join("..", "..", "include", "bevk.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "--fmad=false",                       # the bit-exact paths never want implicit FMA contraction

@@ -1,6 +1,7 @@
 // bevk_api.cu -- C ABI of libbevk.so (see include/bevk.h) over the sm_100a kernels.
 // Host side: argument checks, 3x3 inverses the way OpenCV computes them, device
 // buffer management, the tile-plan compiler, stream ordering.  No CPU fallback.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -19,8 +20,17 @@
 #include "bevk_bev.cuh"
 #include "bevk_gather4.cuh"
 #include "bevk_plan.cuh"
+#include "bevk_bev_tma.cuh"
+#include "bevk_plan_tma.cuh"
 
 using namespace bevk;
+
+#ifndef BEVK_TMA_FS
+#define BEVK_TMA_FS 6144        // bytes of one frame-set's staged source box (plan: larger boxes split / gather)
+#endif
+#ifndef BEVK_TMA_STAGES
+#define BEVK_TMA_STAGES 2
+#endif
 
 
 // ------------------------------------------------------------------ errors
@@ -129,9 +139,27 @@ struct bevk_ctx {
   int bev_grid[6] = {0, 0, 0, 0, 0, 0};   // resident CTAs of k_bev<BAL, NB>: index = 3*BAL + {NB=1:0, 4:1, 8:2}
   DevBuf d_frames, d_ptrs, d_canvas, d_car, d_vsum, d_delta, d_csum;
   DevBuf d_spans, d_bal, d_bal_ptrs;        // BALANCE: sampled row spans per camera, balanced frame copies + their table
-  const void* bal_ptrs_for = nullptr; long long bal_ptrs_n = 0;
+  const void* bal_ptrs_for = nullptr; long long bal_ptrs_n = 0; size_t bal_ptrs_pad = 0;
   DevBuf d_user_ptrs;                       // bevk_bev_run_frames: device copy of the caller's frame table
   std::vector<const void*> user_tab;        // ... and what it currently holds
+  // TMA-staged kernel (bevk_bev_tma.cuh): its plan, and the tensor maps of the frame stacks seen recently
+  bool tma_planned = false;
+  int tma_stage_bytes = 0;
+  long long tma_items = 0, tma_box_bytes = 0, tma_entries = 0, tma_gather_entries = 0;
+  std::vector<int2> tma_shapes;
+  DevBuf d_ttiles, d_titems, d_tlut;
+  struct MapSet { const void* base = nullptr; long long stride = 0, frames = 0; DevBuf d; unsigned long long used = 0; };
+  MapSet maps[4];
+  unsigned long long map_clock = 0;
+  int tma_grid[4] = {0, 0, 0, 0};           // resident CTAs of k_bev_tma<BAL, NB>: index = 2*BAL + {NB=1:0, 4:1}
+  DevBuf d_stack_ptrs;                      // pointer table of a frame stack (BALANCE pre-passes read frames through a table)
+  const void* stack_ptrs_base = nullptr; long long stack_ptrs_stride = 0, stack_ptrs_n = 0;
+  int last_path = 0;                        // 1: k_bev (pointer-table gather), 2: k_bev_tma
+  // CUDA graphs captured from the device-pointer entry points (bevk_graph_*)
+  bool capturing = false;
+  long long capture_launches0 = 0;
+  struct Graph { cudaGraph_t g = nullptr; cudaGraphExec_t x = nullptr; long long kernels = 0; };
+  std::vector<Graph> graphs;
 };
 
 static int use(bevk_ctx* c) {
@@ -181,8 +209,11 @@ int bevk_ctx_destroy(bevk_ctx* c) {
   cudaDeviceSynchronize();   // not c->stream: a caller-owned stream handed to bevk_ctx_set_stream may be gone by now
   for (DevBuf* b : {&c->s_src, &c->s_dst, &c->s_m1, &c->s_m2, &c->s_o1, &c->s_o2, &c->d_tiles, &c->d_items, &c->d_lut,
                     &c->d_hsv, &c->d_frames, &c->d_ptrs, &c->d_canvas, &c->d_car, &c->d_vsum, &c->d_delta, &c->d_csum,
-                    &c->d_spans, &c->d_bal, &c->d_bal_ptrs, &c->d_user_ptrs})
+                    &c->d_spans, &c->d_bal, &c->d_bal_ptrs, &c->d_user_ptrs, &c->d_ttiles, &c->d_titems, &c->d_tlut,
+                    &c->d_stack_ptrs})
     b->release();
+  for (auto& m : c->maps) m.d.release();
+  for (auto& g : c->graphs) { if (g.x) cudaGraphExecDestroy(g.x); if (g.g) cudaGraphDestroy(g.g); }
   for (auto& u : c->und) { u.map1.release(); u.map2.release(); }
   for (auto& k : c->cam) { k.map1.release(); k.map2.release(); }
   cudaEventDestroy(c->ev0);
@@ -213,6 +244,12 @@ int bevk_ctx_set_stream(bevk_ctx* c, void* s) {
 int bevk_ctx_sync(bevk_ctx* c) {
   RET(use(c));
   CU(cudaStreamSynchronize(c->stream));
+  return BEVK_OK;
+}
+
+int bevk_device_pci_bus_id(int device, char* out, int len) {
+  if (!out || len < 16) return fail(BEVK_ERR_ARG, "bus id buffer too small");
+  CU(cudaDeviceGetPCIBusId(out, len, device));
   return BEVK_OK;
 }
 
@@ -354,11 +391,12 @@ int bevk_undistorter_maps(bevk_ctx* c, int slot, int16_t* map1, uint16_t* map2) 
 }
 
 int bevk_undistort(bevk_ctx* c, int slot, const uint8_t* src, int sw, int sh, int64_t sstride, int channels,
-                   uint8_t* dst, int64_t dstride, int interp) {
+                   uint8_t* dst, int dw, int dh, int64_t dstride, int interp) {
   RET(use(c));
   if (slot < 0 || slot >= 8 || !c->und[slot].valid) return fail(BEVK_ERR_ARG, "undistorter slot %d not set", slot);
   Undistorter& u = c->und[slot];
-  const int dw = u.cm.w, dh = u.cm.h;
+  if (dw != u.cm.w || dh != u.cm.h)   // the caller sized dst for another map: never write past it
+    return fail(BEVK_ERR_ARG, "undistorter slot %d holds a %dx%d map, the caller expects %dx%d", slot, u.cm.w, u.cm.h, dw, dh);
   RET(check_image(src, sw, sh, sstride, channels, "src"));
   RET(check_image(dst, dw, dh, dstride, channels, "dst"));
   if (interp != BEVK_INTER_LINEAR && interp != BEVK_INTER_NEAREST) return fail(BEVK_ERR_UNSUPPORTED, "interp %d", interp);
@@ -428,6 +466,9 @@ int bevk_bev_configure(bevk_ctx* c, int n_cam, int fw, int fh, int bw, int bh) {
   c->n_cam = n_cam; c->FW = fw; c->FH = fh; c->BW = bw; c->BH = bh;
   c->bev_interp = BEVK_INTER_LINEAR;
   c->planned = false;
+  c->tma_planned = false;
+  // cached pointer tables are keyed on buffer addresses: a new geometry changes the strides behind the same addresses
+  c->ptrs_for = nullptr; c->bal_ptrs_for = nullptr; c->bal_ptrs_n = 0; c->stack_ptrs_base = nullptr;
   for (auto& k : c->cam) { k.has_maps = false; k.has_mask = false; k.mask.clear(); }
   return BEVK_OK;
 }
@@ -592,6 +633,49 @@ int bevk_bev_finalize(bevk_ctx* c) {
   RET(c->d_hsv.ensure(512 * sizeof(int)));
   CU(cudaMemcpyAsync(c->d_hsv.p, tab.data(), 512 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  // ---- the TMA-staged kernel's plan (frames whose row pitch is a multiple of 16 bytes)
+  c->tma_planned = false;
+  c->tma_stage_bytes = BEVK_TMA_FS;
+  {
+    TmaPlan tp;
+    std::vector<const short*> p1(NC);
+    std::vector<const unsigned short*> p2(NC);
+    std::vector<const uint8_t*> pm(NC);
+    for (int k = 0; k < NC; ++k) { p1[k] = m1[k].data(); p2[k] = m2[k].data(); pm[k] = c->cam[k].mask.data(); }
+    const char* env = getenv("BEVK_TMA");
+    const bool want = !(env && atoi(env) == 0) && ((unsigned)FW * 3u) % 16u == 0;
+    if (want) {
+      build_tma_plan(NC, FW, FH, BW, BH, c->bev_interp == BEVK_INTER_NEAREST, p1.data(), p2.data(), pm.data(), c->tma_stage_bytes, true, tp);
+      RET(c->d_ttiles.ensure(tp.tiles.size() * sizeof(int4)));
+      RET(c->d_titems.ensure(std::max<size_t>(1, tp.items.size()) * sizeof(TmaItem)));
+      RET(c->d_tlut.ensure(std::max<size_t>(1, tp.lut.size()) * sizeof(uint4)));
+      CU(cudaMemcpyAsync(c->d_ttiles.p, tp.tiles.data(), tp.tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+      if (!tp.items.empty()) {
+        CU(cudaMemcpyAsync(c->d_titems.p, tp.items.data(), tp.items.size() * sizeof(TmaItem), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_tlut.p, tp.lut.data(), tp.lut.size() * sizeof(uint4), cudaMemcpyHostToDevice, c->stream));
+      }
+      CU(cudaStreamSynchronize(c->stream));
+      c->tma_shapes = tp.shapes;
+      c->tma_items = (long long)tp.items.size(); c->tma_box_bytes = tp.box_bytes;
+      c->tma_entries = tp.tma_entries; c->tma_gather_entries = tp.gather_entries;
+      for (auto& m : c->maps) m.base = nullptr;   // tensor maps are per shape table
+      c->tma_planned = true;
+    }
+  }
+  if (c->tma_planned && c->tma_grid[0] == 0) {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, c->device));
+    const void* fn[4] = {(const void*)k_bev_tma<false, 1, BEVK_TMA_FS, BEVK_TMA_STAGES>, (const void*)k_bev_tma<false, 4, BEVK_TMA_FS, BEVK_TMA_STAGES>,
+                         (const void*)k_bev_tma<true, 1, BEVK_TMA_FS, BEVK_TMA_STAGES>, (const void*)k_bev_tma<true, 4, BEVK_TMA_FS, BEVK_TMA_STAGES>};
+    const int nb[4] = {1, 4, 1, 4};
+    for (int i = 0; i < 4; ++i) {
+      int per_sm = 0;
+      const size_t smem = bev_tma_smem_bytes(nb[i], BEVK_TMA_FS, BEVK_TMA_STAGES);
+      CU(cudaFuncSetAttribute(fn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn[i], TMA_THREADS, smem));
+      c->tma_grid[i] = std::max(1, per_sm) * prop.multiProcessorCount;
+    }
+  }
   if (c->bev_grid[0] == 0) {   // persistent grid = resident CTAs of each variant
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, c->device));
@@ -619,6 +703,19 @@ int bevk_bev_plan_info(bevk_ctx* c, int64_t* n_tiles, int64_t* n_items, int64_t*
   return BEVK_OK;
 }
 
+int bevk_bev_tma_plan_info(bevk_ctx* c, int64_t* n_items, int64_t* n_shapes, int64_t* box_bytes, int64_t* tma_entries,
+                           int64_t* gather_entries) {
+  RET(use(c));
+  if (!c->planned) return fail(BEVK_ERR_ARG, "bevk_bev_finalize not called");
+  const bool t = c->tma_planned;
+  if (n_items) *n_items = t ? c->tma_items : 0;
+  if (n_shapes) *n_shapes = t ? (int64_t)c->tma_shapes.size() : 0;
+  if (box_bytes) *box_bytes = t ? c->tma_box_bytes : 0;
+  if (tma_entries) *tma_entries = t ? c->tma_entries : 0;
+  if (gather_entries) *gather_entries = t ? c->tma_gather_entries : 0;
+  return BEVK_OK;
+}
+
 int64_t bevk_bev_last_h2d_bytes(bevk_ctx* c) { return c ? c->last_h2d_bytes : 0; }
 
 int bevk_bev_host_copy_bytes(bevk_ctx* c, int flags, int64_t* h2d, int64_t* d2h) {
@@ -636,14 +733,101 @@ int bevk_bev_host_copy_bytes(bevk_ctx* c, int flags, int64_t* h2d, int64_t* d2h)
 }
 
 // ------------------------------------------------------------------ BEV engine: run
-static int run_device(bevk_ctx* c, const void* d_srcs, int batch, const void* d_car, int flags, void* d_out, int cam_lo,
-                      int cam_hi) {
+// Where the frames of a call live: a device table of frame pointers (any layout), or a frame STACK (frame i at
+// base + i * stride), which is what the TMA-staged kernel's 3-D tensor maps describe.
+struct FrameSrc {
+  const void* table = nullptr;
+  const uint8_t* base = nullptr;
+  long long stride = 0;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// Tensor maps (one per box shape of the plan) of the frame stack (base, stride, frames): uint32[frames][FH][pitch/4].
+static int stack_maps(bevk_ctx* c, const uint8_t* base, long long stride, long long frames, const uint8_t** d_maps) {
+  bevk_ctx::MapSet* slot = &c->maps[0];
+  for (auto& m : c->maps) {
+    if (m.base == base && m.stride == stride && m.frames >= frames) { m.used = ++c->map_clock; *d_maps = m.d.as<uint8_t>(); return BEVK_OK; }
+    if (m.used < slot->used) slot = &m;
+  }
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return fail(BEVK_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+  static_assert(sizeof(CUtensorMap) == TMA_DESC_BYTES, "tensor map size");
+  const size_t n = c->tma_shapes.size();
+  std::vector<CUtensorMap> maps(std::max<size_t>(1, n));
+  const cuuint64_t dims[3] = {(cuuint64_t)c->FW * 3u / 4u, (cuuint64_t)c->FH, (cuuint64_t)frames};
+  const cuuint64_t strides[2] = {(cuuint64_t)c->FW * 3u, (cuuint64_t)stride};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  for (size_t i = 0; i < n; ++i) {
+    const cuuint32_t box[3] = {(cuuint32_t)c->tma_shapes[i].x, (cuuint32_t)c->tma_shapes[i].y, 1};
+    const CUresult r = enc(&maps[i], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return fail(BEVK_ERR_CUDA, "cuTensorMapEncodeTiled(box %u x %u words, stride %lld) failed: %d", box[0], box[1], stride, (int)r);
+  }
+  // the slot being replaced may still be read by launches in flight on this stream: stream order protects it
+  RET(slot->d.ensure(maps.size() * sizeof(CUtensorMap)));
+  CU(cudaMemcpyAsync(slot->d.p, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));   // maps is a stack-lifetime staging vector
+  slot->base = base; slot->stride = stride; slot->frames = frames; slot->used = ++c->map_clock;
+  *d_maps = slot->d.as<uint8_t>();
+  return BEVK_OK;
+}
+
+__global__ void k_fill_ptrs(const uint8_t** table, const uint8_t* base, long long stride, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) table[i] = base + (long long)i * stride;
+}
+
+// pointer table of a frame stack (the BALANCE pre-passes and the round-1 gather kernel read frames through a table)
+static int stack_table(bevk_ctx* c, const uint8_t* base, long long stride, int n, const void** table) {
+  RET(c->d_stack_ptrs.ensure(sizeof(void*) * (size_t)n));
+  if (c->stack_ptrs_base != base || c->stack_ptrs_stride != stride || c->stack_ptrs_n < n) {
+    k_fill_ptrs<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_stack_ptrs.as<const uint8_t*>(), base, stride, n);
+    LAUNCHED(c);
+    c->stack_ptrs_base = base; c->stack_ptrs_stride = stride; c->stack_ptrs_n = n;
+  }
+  *table = c->d_stack_ptrs.p;
+  return BEVK_OK;
+}
+
+template <bool BAL>
+static int launch_bev_tma(bevk_ctx* c, const TmaParams& P, int nbu) {
+  const long long units = c->n_tiles * ((P.batch + nbu - 1) / nbu);
+  const int variant = (BAL ? 2 : 0) + (nbu == 4 ? 1 : 0);
+  const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(units, c->tma_grid[variant]));
+  const size_t smem = bev_tma_smem_bytes(nbu, BEVK_TMA_FS, BEVK_TMA_STAGES);
+  if (nbu == 4) k_bev_tma<BAL, 4, BEVK_TMA_FS, BEVK_TMA_STAGES><<<blocks, TMA_THREADS, smem, c->stream>>>(P);
+  else k_bev_tma<BAL, 1, BEVK_TMA_FS, BEVK_TMA_STAGES><<<blocks, TMA_THREADS, smem, c->stream>>>(P);
+  LAUNCHED(c);
+  return BEVK_OK;
+}
+
+static int run_device(bevk_ctx* c, FrameSrc src, int batch, const void* d_car, int flags, void* d_out, int cam_lo, int cam_hi) {
   if (!c->planned) return fail(BEVK_ERR_ARG, "bevk_bev_finalize not called");
-  if (!d_srcs || !d_out) return fail(BEVK_ERR_ARG, "null device pointer");
+  if ((!src.table && !src.base) || !d_out) return fail(BEVK_ERR_ARG, "null device pointer");
   if (batch < 1 || batch > 65535) return fail(BEVK_ERR_ARG, "batch %d out of range [1,65535]", batch);
   const bool bal = (flags & BEVK_FLAG_BALANCE) != 0;
+  const int nf = batch * c->n_cam;
+  if (bal && nf > 65535) return fail(BEVK_ERR_ARG, "batch %d x %d cameras exceeds the 65535 frames of a BALANCE call", batch, c->n_cam);
   BevParams P{};
-  P.srcs = reinterpret_cast<const uint8_t* const*>(d_srcs);
   P.n_cam = c->n_cam; P.FW = c->FW; P.FH = c->FH; P.pitch = (unsigned)c->FW * 3u;
   P.tiles = c->d_tiles.as<int4>(); P.items = c->d_items.as<BevItem>(); P.lut = c->d_lut.as<uint4>();
   P.out = reinterpret_cast<uint8_t*>(d_out); P.BW = c->BW; P.BH = c->BH;
@@ -654,21 +838,20 @@ static int run_device(bevk_ctx* c, const void* d_srcs, int batch, const void* d_
   // frame-sets per work unit: 4 amortises the LUT decode over a batch; 1 for single frames
   int nbu = batch >= 4 ? 4 : 1;
   if (c->nb_override) nbu = c->nb_override;
-  const long long units = c->n_tiles * ((batch + nbu - 1) / nbu);
-  const int variant = (bal ? 3 : 0) + (nbu == 8 ? 2 : (nbu == 4 ? 1 : 0));
-  const unsigned bev_blocks = (unsigned)std::max<long long>(1, std::min<long long>(units, c->bev_grid[variant]));
-  const size_t bev_smem = bev_smem_bytes(bal, nbu);
-  if (c->timed) CU(cudaEventRecord(c->ev0, c->stream));
+  if (c->timed && !c->capturing) CU(cudaEventRecord(c->ev0, c->stream));
+  FrameSrc gsrc = src;                         // what the fused gather reads
   if (bal) {
-    const int nf = batch * c->n_cam;
     RET(c->d_vsum.ensure((size_t)nf * 8));
     RET(c->d_delta.ensure((size_t)nf * 4));
     RET(c->d_csum.ensure((size_t)batch * 24));
     CU(cudaMemsetAsync(c->d_vsum.p, 0, (size_t)nf * 8, c->stream));
     CU(cudaMemsetAsync(c->d_csum.p, 0, (size_t)batch * 24, c->stream));
+    const void* table = src.table;
+    if (!table) RET(stack_table(c, src.base, src.stride, nf, &table));
+    const uint8_t* const* srcs = reinterpret_cast<const uint8_t* const*>(table);
     const long long frame_bytes = (long long)P.pitch * c->FH;
     const int blocks = (int)std::max<long long>(1, std::min<long long>(148 * 4 / std::max(1, std::min(nf, 64)) + 1, frame_bytes / (48 * 256) + 1));
-    k_vsum<<<dim3(blocks, nf), 256, 0, c->stream>>>(P.srcs, frame_bytes, c->d_vsum.as<unsigned long long>());
+    k_vsum<<<dim3(blocks, nf), 256, 0, c->stream>>>(srcs, frame_bytes, c->d_vsum.as<unsigned long long>());
     LAUNCHED(c);
     k_delta<<<(batch + 127) / 128, 128, 0, c->stream>>>(c->d_vsum.as<unsigned long long>(), c->n_cam, batch,
                                                          (double)c->FW * (double)c->FH, c->d_delta.as<int>());
@@ -678,40 +861,78 @@ static int run_device(bevk_ctx* c, const void* d_srcs, int batch, const void* d_
     const size_t fpad = ((size_t)frame_bytes + 255) & ~size_t(255);
     RET(c->d_bal.ensure(fpad * nf));
     RET(c->d_bal_ptrs.ensure(sizeof(void*) * nf));
-    if (c->bal_ptrs_for != c->d_bal.p || c->bal_ptrs_n != nf) {
-      std::vector<uint8_t*> bp((size_t)nf);
-      for (int i = 0; i < nf; ++i) bp[i] = c->d_bal.as<uint8_t>() + (size_t)i * fpad;
-      CU(cudaMemcpyAsync(c->d_bal_ptrs.p, bp.data(), bp.size() * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
-      CU(cudaStreamSynchronize(c->stream));   // bp is a stack-lifetime staging vector
-      c->bal_ptrs_for = c->d_bal.p; c->bal_ptrs_n = nf;
+    if (c->bal_ptrs_for != c->d_bal.p || c->bal_ptrs_n != nf || c->bal_ptrs_pad != fpad) {
+      k_fill_ptrs<<<(nf + 255) / 256, 256, 0, c->stream>>>(c->d_bal_ptrs.as<const uint8_t*>(), c->d_bal.as<uint8_t>(), (long long)fpad, nf);
+      LAUNCHED(c);
+      c->bal_ptrs_for = c->d_bal.p; c->bal_ptrs_n = nf; c->bal_ptrs_pad = fpad;
     }
-    k_lum_spans<<<dim3(c->FH, nf), 128, 0, c->stream>>>(P.srcs, c->d_bal_ptrs.as<uint8_t*>(), c->d_spans.as<int2>(), c->n_cam,
+    k_lum_spans<<<dim3(c->FH, nf), 128, 0, c->stream>>>(srcs, c->d_bal_ptrs.as<uint8_t*>(), c->d_spans.as<int2>(), c->n_cam,
                                                        c->FW, c->FH, c->d_delta.as<int>(), c->d_hsv.as<int>());
     LAUNCHED(c);
-    P.srcs = c->d_bal_ptrs.as<const uint8_t*>();
+    gsrc.table = c->d_bal_ptrs.p; gsrc.base = c->d_bal.as<uint8_t>(); gsrc.stride = (long long)fpad;
     P.csum = c->d_csum.as<unsigned long long>();
-    if (nbu == 8) k_bev<true, 8><<<bev_blocks, 256, bev_smem, c->stream>>>(P);
-    else if (nbu == 4) k_bev<true, 4><<<bev_blocks, 256, bev_smem, c->stream>>>(P);
-    else k_bev<true, 1><<<bev_blocks, 256, bev_smem, c->stream>>>(P);
+  }
+  // TMA-staged kernel for frame stacks (16-byte aligned base and stride); pointer-table gather otherwise
+  const bool use_tma = c->tma_planned && gsrc.base && (reinterpret_cast<uintptr_t>(gsrc.base) & 15) == 0 && (gsrc.stride & 15) == 0 &&
+                       gsrc.stride >= (long long)P.pitch * c->FH && (nbu == 1 || nbu == 4);
+  if (use_tma) {
+    TmaParams T{};
+    RET(stack_maps(c, gsrc.base, gsrc.stride, nf, &T.maps));
+    T.base = gsrc.base; T.frame_stride = gsrc.stride;
+    T.n_cam = P.n_cam; T.FW = P.FW; T.FH = P.FH; T.pitch = P.pitch;
+    T.tiles = c->d_ttiles.as<int4>(); T.items = c->d_titems.as<TmaItem>(); T.lut = c->d_tlut.as<uint4>();
+    T.n_tiles = P.n_tiles; T.batch = batch; T.out = P.out; T.BW = P.BW; T.BH = P.BH; T.canvas_bytes = P.canvas_bytes;
+    T.car = P.car; T.csum = P.csum; T.cam_lo = cam_lo; T.cam_hi = cam_hi;
+    if (bal) RET(launch_bev_tma<true>(c, T, nbu)); else RET(launch_bev_tma<false>(c, T, nbu));
+    c->last_path = 2;
+  } else {
+    if (!gsrc.table) RET(stack_table(c, gsrc.base, gsrc.stride, nf, &gsrc.table));
+    P.srcs = reinterpret_cast<const uint8_t* const*>(gsrc.table);
+    const long long units = c->n_tiles * ((batch + nbu - 1) / nbu);
+    const int variant = (bal ? 3 : 0) + (nbu == 8 ? 2 : (nbu == 4 ? 1 : 0));
+    const unsigned bev_blocks = (unsigned)std::max<long long>(1, std::min<long long>(units, c->bev_grid[variant]));
+    const size_t bev_smem = bev_smem_bytes(bal, nbu);
+    if (bal) {
+      if (nbu == 8) k_bev<true, 8><<<bev_blocks, 256, bev_smem, c->stream>>>(P);
+      else if (nbu == 4) k_bev<true, 4><<<bev_blocks, 256, bev_smem, c->stream>>>(P);
+      else k_bev<true, 1><<<bev_blocks, 256, bev_smem, c->stream>>>(P);
+    } else {
+      if (nbu == 8) k_bev<false, 8><<<bev_blocks, 256, bev_smem, c->stream>>>(P);
+      else if (nbu == 4) k_bev<false, 4><<<bev_blocks, 256, bev_smem, c->stream>>>(P);
+      else k_bev<false, 1><<<bev_blocks, 256, bev_smem, c->stream>>>(P);
+    }
     LAUNCHED(c);
+    c->last_path = 1;
+  }
+  if (bal) {
     const int gblocks = (int)std::max<long long>(1, std::min<long long>(P.canvas_bytes / (12 * 256) + 1, 148 * 8 / std::max(1, std::min(batch, 64)) + 1));
     k_gain<<<dim3(gblocks, batch), 256, 0, c->stream>>>(P.out, P.canvas_bytes, (double)c->BW * (double)c->BH,
                                                         c->d_csum.as<unsigned long long>(), P.car);
     LAUNCHED(c);
-  } else {
-    if (nbu == 8) k_bev<false, 8><<<bev_blocks, 256, bev_smem, c->stream>>>(P);
-    else if (nbu == 4) k_bev<false, 4><<<bev_blocks, 256, bev_smem, c->stream>>>(P);
-    else k_bev<false, 1><<<bev_blocks, 256, bev_smem, c->stream>>>(P);
-    LAUNCHED(c);
   }
-  if (c->timed) CU(cudaEventRecord(c->ev1, c->stream));
+  if (c->timed && !c->capturing) CU(cudaEventRecord(c->ev1, c->stream));
   return BEVK_OK;
 }
+
+static FrameSrc table_src(const void* d_srcs) { FrameSrc s; s.table = d_srcs; return s; }
+static FrameSrc stack_src(const void* base, long long stride) { FrameSrc s; s.base = reinterpret_cast<const uint8_t*>(base); s.stride = stride; return s; }
 
 int bevk_bev_run_device(bevk_ctx* c, const void* d_srcs, int batch, const void* d_car, int flags, void* d_out) {
   RET(use(c));
   c->timed = true;
-  return run_device(c, d_srcs, batch, d_car, flags, d_out, 0, BEVK_MAX_CAMERAS);
+  return run_device(c, table_src(d_srcs), batch, d_car, flags, d_out, 0, BEVK_MAX_CAMERAS);
+}
+
+// frames[i] == frames[0] + i * stride with a 16-byte friendly stride?  (a frame stack: the TMA-staged kernel applies)
+static bool affine_table(const void* const* frames, size_t n, long long* stride) {
+  const uintptr_t b = reinterpret_cast<uintptr_t>(frames[0]);
+  if (n == 1) { *stride = 1ll << 32; return (b & 15) == 0; }   // a single frame is a stack of one
+  const long long st = (long long)(reinterpret_cast<uintptr_t>(frames[1]) - b);
+  if (st <= 0 || (st & 15) || (b & 15)) return false;
+  for (size_t i = 2; i < n; ++i)
+    if (reinterpret_cast<uintptr_t>(frames[i]) != b + (uintptr_t)st * i) return false;
+  *stride = st;
+  return true;
 }
 
 int bevk_bev_run_frames(bevk_ctx* c, const void* const* frames, int batch, const void* d_car, int flags, void* d_out) {
@@ -722,6 +943,11 @@ int bevk_bev_run_frames(bevk_ctx* c, const void* const* frames, int batch, const
   const size_t n = (size_t)batch * c->n_cam;
   for (size_t i = 0; i < n; ++i)
     if (!frames[i] || (reinterpret_cast<uintptr_t>(frames[i]) & 3)) return fail(BEVK_ERR_ARG, "frame %zu null or not 4-byte aligned", i);
+  long long stride = 0;
+  if (c->tma_planned && affine_table(frames, n, &stride)) {   // no table upload at all
+    c->timed = true;
+    return run_device(c, stack_src(frames[0], stride), batch, d_car, flags, d_out, 0, BEVK_MAX_CAMERAS);
+  }
   if (c->user_tab.size() != n || memcmp(c->user_tab.data(), frames, n * sizeof(void*)) != 0) {
     RET(c->d_user_ptrs.ensure(n * sizeof(void*)));
     c->user_tab.assign(frames, frames + n);
@@ -733,14 +959,38 @@ int bevk_bev_run_frames(bevk_ctx* c, const void* const* frames, int batch, const
     }
   }
   c->timed = true;
-  return run_device(c, c->d_user_ptrs.p, batch, d_car, flags, d_out, 0, BEVK_MAX_CAMERAS);
+  return run_device(c, table_src(c->d_user_ptrs.p), batch, d_car, flags, d_out, 0, BEVK_MAX_CAMERAS);
 }
+
+static int check_stack(bevk_ctx* c, const void* d_frames, int64_t frame_stride) {
+  if (!d_frames) return fail(BEVK_ERR_ARG, "null frame stack");
+  if (reinterpret_cast<uintptr_t>(d_frames) & 3) return fail(BEVK_ERR_ARG, "frame stack not 4-byte aligned");
+  if (frame_stride < (int64_t)c->FW * c->FH * 3 || (frame_stride & 3)) return fail(BEVK_ERR_ARG, "frame_stride %lld smaller than a frame or not a multiple of 4", (long long)frame_stride);
+  return BEVK_OK;
+}
+
+int bevk_bev_run_stack(bevk_ctx* c, const void* d_frames, int64_t frame_stride, int batch, const void* d_car, int flags, void* d_out) {
+  RET(use(c));
+  RET(check_stack(c, d_frames, frame_stride));
+  c->timed = true;
+  return run_device(c, stack_src(d_frames, frame_stride), batch, d_car, flags, d_out, 0, BEVK_MAX_CAMERAS);
+}
+
+int bevk_bev_run_stack_cams(bevk_ctx* c, const void* d_frames, int64_t frame_stride, int batch, int cam_lo, int cam_hi, void* d_out) {
+  RET(use(c));
+  RET(check_stack(c, d_frames, frame_stride));
+  if (cam_lo < 0 || cam_hi > c->n_cam || cam_lo > cam_hi) return fail(BEVK_ERR_ARG, "bad camera range [%d,%d)", cam_lo, cam_hi);
+  c->timed = true;
+  return run_device(c, stack_src(d_frames, frame_stride), batch, nullptr, 0, d_out, cam_lo, cam_hi);
+}
+
+int bevk_bev_last_path(bevk_ctx* c) { return c ? c->last_path : 0; }
 
 int bevk_bev_run_device_cams(bevk_ctx* c, const void* d_srcs, int batch, int cam_lo, int cam_hi, void* d_out) {
   RET(use(c));
   if (cam_lo < 0 || cam_hi > c->n_cam || cam_lo > cam_hi) return fail(BEVK_ERR_ARG, "bad camera range [%d,%d)", cam_lo, cam_hi);
   c->timed = true;
-  return run_device(c, d_srcs, batch, nullptr, 0, d_out, cam_lo, cam_hi);
+  return run_device(c, table_src(d_srcs), batch, nullptr, 0, d_out, cam_lo, cam_hi);
 }
 
 int bevk_sat_sum_device(bevk_ctx* c, const void* const* parts, int n, uint64_t bytes, const void* d_car, void* d_out) {
@@ -866,7 +1116,9 @@ int bevk_bev_run(bevk_ctx* c, const uint8_t* const* srcs, int64_t src_stride, in
     c->timed = false;
     uint8_t* dcanvas = c->d_canvas.as<uint8_t>() + (size_t)half * chunk * cbytes;
     const void* dptrs = c->d_ptrs.as<const uint8_t*>() + (size_t)half * chunk * set_frames;
-    RET(run_device(c, dptrs, nb, car ? c->d_car.p : nullptr, flags, dcanvas, 0, BEVK_MAX_CAMERAS));
+    FrameSrc fsrc = stack_src(dframes, (long long)fpad);   // the staging buffers are a frame stack: TMA-staged kernel
+    fsrc.table = dptrs;
+    RET(run_device(c, fsrc, nb, car ? c->d_car.p : nullptr, flags, dcanvas, 0, BEVK_MAX_CAMERAS));
     CU(cudaEventRecord(c->ev_free[half], c->stream));               // frames of this half are free again
     CU(cudaMemcpyAsync(out + (size_t)b0 * cbytes, dcanvas, cbytes * nb, cudaMemcpyDeviceToHost, c->stream));
   }
@@ -961,6 +1213,59 @@ int bevk_luminance_balance(bevk_ctx* c, const uint8_t* const* imgs, int n, int w
   for (int i = 0; i < n; ++i)
     CU(cudaMemcpyAsync(outs[i], ptrs[BEVK_MAX_CAMERAS + i], fbytes, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));   // also keeps the stack-resident ptrs[] alive long enough
+  return BEVK_OK;
+}
+
+// ------------------------------------------------------------------ CUDA graphs
+// Stream capture of whatever the device-pointer entry points enqueue between begin and end; replayed with one call.
+int bevk_graph_begin(bevk_ctx* c) {
+  RET(use(c));
+  if (c->capturing) return fail(BEVK_ERR_ARG, "a capture is already open on this context");
+  CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  c->capturing = true;
+  c->capture_launches0 = c->launches;
+  return BEVK_OK;
+}
+
+int bevk_graph_end(bevk_ctx* c, int* graph_id) {
+  RET(use(c));
+  if (!c->capturing) return fail(BEVK_ERR_ARG, "bevk_graph_begin was not called");
+  c->capturing = false;
+  bevk_ctx::Graph g;
+  cudaError_t e = cudaStreamEndCapture(c->stream, &g.g);
+  if (e != cudaSuccess || !g.g) {
+    cudaGetLastError();
+    return fail(BEVK_ERR_CUDA, "stream capture failed (%s): a call inside the capture allocated or synchronised -- run the same "
+                               "calls once before capturing so that every buffer and table exists", cudaGetErrorString(e));
+  }
+  e = cudaGraphInstantiate(&g.x, g.g, 0);
+  if (e != cudaSuccess) { cudaGraphDestroy(g.g); return fail(BEVK_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+  g.kernels = c->launches - c->capture_launches0;
+  c->launches = c->capture_launches0;            // nothing ran yet: replays are counted by bevk_graph_launch
+  size_t slot = 0;
+  while (slot < c->graphs.size() && c->graphs[slot].x) ++slot;
+  if (slot == c->graphs.size()) c->graphs.push_back(g); else c->graphs[slot] = g;
+  if (graph_id) *graph_id = (int)slot;
+  return BEVK_OK;
+}
+
+int bevk_graph_launch(bevk_ctx* c, int graph_id, int times) {
+  RET(use(c));
+  if (graph_id < 0 || (size_t)graph_id >= c->graphs.size() || !c->graphs[graph_id].x) return fail(BEVK_ERR_ARG, "no graph %d", graph_id);
+  if (times < 1) return fail(BEVK_ERR_ARG, "times must be >= 1");
+  if (c->capturing) return fail(BEVK_ERR_ARG, "cannot launch a graph inside a capture");
+  for (int i = 0; i < times; ++i) CU(cudaGraphLaunch(c->graphs[graph_id].x, c->stream));
+  c->launches += (long long)times * c->graphs[graph_id].kernels;
+  return BEVK_OK;
+}
+
+int bevk_graph_destroy(bevk_ctx* c, int graph_id) {
+  RET(use(c));
+  if (graph_id < 0 || (size_t)graph_id >= c->graphs.size() || !c->graphs[graph_id].x) return fail(BEVK_ERR_ARG, "no graph %d", graph_id);
+  CU(cudaStreamSynchronize(c->stream));
+  cudaGraphExecDestroy(c->graphs[graph_id].x);
+  cudaGraphDestroy(c->graphs[graph_id].g);
+  c->graphs[graph_id] = bevk_ctx::Graph();
   return BEVK_OK;
 }
 

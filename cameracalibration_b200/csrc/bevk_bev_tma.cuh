@@ -1,0 +1,415 @@
+// bevk_bev_tma.cuh -- the fused surround-BEV kernel with TMA-staged source boxes (sm_100a).
+//
+// Same reference path as bevk_bev.cuh (SurroundBirdEyeView/surroundBEV.py:312-325: cv2.remap per camera :116-117,
+// Mask / BlendMask.__call__ :161-162 / :279-280, the saturating cv2.add chain :318-320, car overlay :323-324), same
+// arithmetic, different memory movement:
+//
+//   * the frames of a batch are one 3-D tensor  uint32[frame][row][pitch/4]  (frames at a uniform stride); for every
+//     work item -- (canvas tile, camera, range of 8-line strips) -- the plan compiler (bevk_plan_tma.cuh) knows the
+//     bounding box of the source words its taps read, and a producer warp fetches that box for each of the NB
+//     frame-sets of the unit with ONE cp.async.bulk.tensor.3d (SASS UTMALDG) into a ring of shared-memory stages,
+//     completion on an mbarrier.  Taps outside the frame need no special path: TMA zero-fills out-of-bounds words,
+//     which is exactly cv2.remap's BORDER_CONSTANT 0.
+//   * the eight consumer warps read their taps from shared memory (LDS with immediate offsets for frame-set and
+//     word; ~1.6 bank wavefronts per load instead of 4.4 L1 tag look-ups per global load, profiles/), and release
+//     the stage through a second mbarrier;
+//   * strips whose box would not fit a stage (heavily minified near field, discontinuities of the LUT) are GATHER
+//     items: their entries carry global byte offsets and take the 32-bit global loads of the round-1 kernel.
+//
+// LUT entry (16 B, thread order t = warp*32 + lane, group k: canvas line k*8 + warp, position lane along it):
+//   .x  TMA item: byte offset of the aligned word holding tap (sy,sx) inside the frame-set's staged box | the same
+//       for row sy+1 << 16;   GATHER item: byte offset of tap (sy,sx) in the frame (slow entries: sx | sy << 16)
+//   .y  w00' | w10' << 16,  .z  w01' | w11' << 16   with w' = min(64 w, 65535): the DP2A sums carry
+//       64 (sum w p + 512), so byte 2 of each sum is the interpolated channel -- no shifts
+//   .w  blend multiplier 257*mask+1 (17 bits) | (3 sx mod 4) << 17 | fraction << 19 | T_ACTIVE | T_SLOW
+#pragma once
+#include "bevk_bev.cuh"
+
+namespace bevk {
+
+constexpr unsigned T_ACTIVE = 1u << 29, T_SLOW = 1u << 30;
+constexpr int ITEM_GATHER = 1, ITEM_NOSAT = 2, ITEM_FULL = 4;
+constexpr int TMA_CONSUMERS = 256, TMA_THREADS = TMA_CONSUMERS + 32;
+constexpr int TMA_DESC_BYTES = 128;   // sizeof(CUtensorMap)
+
+struct __align__(16) TmaItem {   // 32 B, read as two 16-byte words
+  int lut_block;                 // LUT block of this (tile, camera): entries [lut_block*1024, +1024)
+  short cam; unsigned char orient, flags;
+  unsigned char k0, k1; unsigned short shape;   // entry groups [k0,k1); index of the box shape's tensor map
+  int xw;                        // box origin: word column (may be negative) ...
+  int y;                         // ... and row; TMA zero-fills what lies outside the frame
+  unsigned tx_bytes;             // bytes the box of ONE frame-set delivers
+  int pad0, pad1;
+};
+static_assert(sizeof(TmaItem) == 32, "TmaItem is read as two int4");
+
+struct TmaParams {
+  const uint8_t* maps;           // [n_shapes] CUtensorMap (128 B each) in global memory
+  const uint8_t* base;           // frame 0 of the stack (GATHER items, slow entries)
+  long long frame_stride;        // bytes between consecutive frames
+  int n_cam, FW, FH;
+  unsigned pitch;
+  const int4* tiles;             // x0, y0, first item, item count
+  const TmaItem* items;
+  const uint4* lut;
+  int n_tiles, batch;
+  uint8_t* out; int BW, BH; long long canvas_bytes;
+  const uint8_t* car;
+  unsigned long long* csum;
+  int cam_lo, cam_hi;
+};
+
+// The six words of one entry -> three sums whose byte 2 is the interpolated channel.
+__host__ __device__ __forceinline__ void interp_sums(unsigned sh8, unsigned wl, unsigned wr, unsigned a0, unsigned a1, unsigned a2,
+                                                     unsigned b0, unsigned b1, unsigned b2, unsigned& sb, unsigned& sg, unsigned& sr) {
+  const unsigned A = lane_funnel_r(a0, a1, sh8), A2 = lane_funnel_r(a1, a2, sh8);   // B0 G0 R0 B1 | G1 R1 . .
+  const unsigned B = lane_funnel_r(b0, b1, sh8), B2 = lane_funnel_r(b1, b2, sh8);   // same, source row + 1
+  const unsigned v0 = lane_perm(A, B, 0x5140);     // B0 B0' G0 G0'
+  const unsigned v1 = lane_perm(A, B, 0x7362);     // R0 R0' B1 B1'
+  const unsigned v2 = lane_perm(A2, B2, 0x5140);   // G1 G1' R1 R1'
+  sb = lane_dp2a_hi(wr, v1, lane_dp2a_lo(wl, v0, 32768u));
+  sg = lane_dp2a_lo(wr, v2, lane_dp2a_hi(wl, v0, 32768u));
+  sr = lane_dp2a_hi(wr, v2, lane_dp2a_lo(wl, v1, 32768u));
+}
+
+// BlendMask.__call__ / Mask.__call__ in exact integer form (bevk_bev.cuh header), then pack B | G<<8 | R<<16.
+// FULL: every weight of the item is 255 (multiplier 65536): the weighted value is the value.
+template <bool FULL>
+__host__ __device__ __forceinline__ unsigned weight_pack(unsigned sb, unsigned sg, unsigned sr, unsigned wm) {
+  if (FULL) return lane_perm(lane_perm(sb, sg, 0x0062), sr, 0x7610);
+  const unsigned ob = (sb >> 16) * wm, og = (sg >> 16) * wm, orr = (sr >> 16) * wm;   // < 2^24, byte 2 is the result
+  return lane_perm(lane_perm(ob, og, 0x0062), orr, 0x7610);
+}
+
+__host__ __device__ __forceinline__ unsigned interp_v(unsigned sh8, unsigned wl, unsigned wr, unsigned wm, unsigned a0, unsigned a1,
+                                                      unsigned a2, unsigned b0, unsigned b1, unsigned b2) {
+  unsigned sb, sg, sr;
+  interp_sums(sh8, wl, wr, a0, a1, a2, b0, b1, b2, sb, sg, sr);
+  return weight_pack<false>(sb, sg, sr, wm);
+}
+
+// DP2A weight pairs of a 10-bit fraction (fy*32 + fx), scaled by 64 (see header)
+__host__ __device__ __forceinline__ void scaled_weights(unsigned frac, unsigned& wl, unsigned& wr) {
+  const unsigned fx = frac & 31u, fy = (frac >> 5) & 31u;
+  const unsigned w11 = fx * fy, w01 = (fx << 5) - w11, w10 = (fy << 5) - w11, w00 = 1024u - (fx << 5) - (fy << 5) + w11;
+  const unsigned s00 = w00 == 1024u ? 65535u : w00 << 6;   // (65535 p + 32768) >> 16 == p for p < 32768
+  wl = s00 | (w10 << 22);
+  wr = (w01 << 6) | (w11 << 22);
+}
+
+#ifdef __CUDACC__
+// ---- mbarrier / TMA primitives (PTX ISA 8.x, sm_90+) ---------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D_%=;\n\t"
+      "bra W_%=;\n\t"
+      "D_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const void* map, int x, int y, int z, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+__device__ __forceinline__ unsigned lds32(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+// Predicated load: the destination keeps whatever it held when `pred` is 0.  Used for the third word of a tap pair,
+// which only pairs starting at byte 3 of a word read (interp_sums never looks at it otherwise).
+__device__ __forceinline__ unsigned lds32_if(unsigned addr, unsigned pred) {
+  unsigned v;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u32 %0, [%1];\n\t}" : "=r"(v) : "r"(addr), "r"(pred));
+  return v;
+}
+__device__ __forceinline__ void sts32(unsigned addr, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory"); }
+
+#ifndef BEVK_TMA_MIN_CTAS
+#define BEVK_TMA_MIN_CTAS 3
+#endif
+
+constexpr size_t bev_tma_smem_bytes(int nb, int fs, int stages) {
+  return (size_t)stages * nb * fs + (size_t)nb * ACC_WORDS * 4 + (size_t)stages * 16 + 1024;   // + alignment slack
+}
+
+// GATHER items (boxes that do not fit a stage): one entry applied to the NB frame-sets of the unit, taps from global
+// memory as in the round-1 kernel.  `aa`: shared address of the entry's accumulator word of frame-set 0.
+template <int NB>
+__device__ __forceinline__ void gather_entry(const TmaParams& P, const uint4 e, unsigned aa, bool first, bool nosat,
+                                             const uint8_t* frame0, long long set_stride) {
+  if (!(e.w & T_ACTIVE)) {
+    if (first) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) sts32(aa + j * ACC_WORDS * 4, 0u);
+    }
+    return;
+  }
+  if (e.w & T_SLOW) {   // out-of-frame taps: per-tap checked path
+    const SlowGeo geo = {P.pitch, P.FW, P.FH};
+    const unsigned ew = (e.w & 0x1ffffu) | (((e.w >> 19) & 1023u) << 17);   // sample_slow's layout: weight | fraction << 17
+#pragma unroll 1
+    for (int j = 0; j < NB; ++j) {
+      unsigned v = sample_slow(geo, frame0 + j * set_stride, e.x, ew);
+      if (!first) v = sat_add_bgr(v, lds32(aa + j * ACC_WORDS * 4));
+      sts32(aa + j * ACC_WORDS * 4, v);
+    }
+    return;
+  }
+  const unsigned sh8 = (e.w >> 14) & 24u, wm = e.w & 0x1ffffu, off_al = e.x & ~3u;
+  const bool third = sh8 == 24u;
+#pragma unroll 2
+  for (int j = 0; j < NB; ++j) {
+    const uint8_t* q0 = frame0 + j * set_stride + off_al;
+    const uint8_t* q1 = q0 + P.pitch;
+    const unsigned a0 = ldg32(q0), a1 = ldg32(q0 + 4), a2 = third ? ldg32(q0 + 8) : 0u;
+    const unsigned b0 = ldg32(q1), b1 = ldg32(q1 + 4), b2 = third ? ldg32(q1 + 8) : 0u;
+    unsigned sb, sg, sr;
+    interp_sums(sh8, e.y, e.z, a0, a1, a2, b0, b1, b2, sb, sg, sr);
+    unsigned v = weight_pack<false>(sb, sg, sr, wm);
+    if (!first) {
+      const unsigned old = lds32(aa + j * ACC_WORDS * 4);
+      v = nosat ? v + old : sat_add_bgr(v, old);                          // cv2.add chain, reference camera order
+    }
+    sts32(aa + j * ACC_WORDS * 4, v);
+  }
+}
+
+// TMA items: the groups [k0,k1) of one LUT block applied to the NB staged boxes.  FIRST: this camera stores (zeros where
+// its mask is 0), later cameras add; FULL: every weight of the item is 255.
+template <int NB, int FS, bool FIRST, bool FULL>
+__device__ __forceinline__ void tma_item(const uint4* __restrict__ L, int k0, int k1, unsigned sbase, unsigned aa, unsigned astep,
+                                         bool nosat) {
+  L += k0 * 256;
+  aa += k0 * astep;
+  uint4 nxt = __ldg(L);
+#pragma unroll 1
+  for (int k = k0; k < k1; ++k, aa += astep) {
+    const uint4 e = nxt;
+    L += 256;
+    if (k + 1 < k1) nxt = __ldg(L);
+    if (!(e.w & T_ACTIVE)) {
+      if (FIRST) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) sts32(aa + j * ACC_WORDS * 4, 0u);
+      }
+      continue;
+    }
+    const unsigned o0 = sbase + (e.x & 0xffffu), o1 = sbase + (e.x >> 16);
+    const unsigned sh8 = (e.w >> 14) & 24u, wm = e.w & 0x1ffffu, third = sh8 == 24u;
+    unsigned a0[NB], a1[NB], a2[NB], b0[NB], b1[NB], b2[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      a0[j] = lds32(o0 + j * FS); a1[j] = lds32(o0 + j * FS + 4); a2[j] = lds32_if(o0 + j * FS + 8, third);
+      b0[j] = lds32(o1 + j * FS); b1[j] = lds32(o1 + j * FS + 4); b2[j] = lds32_if(o1 + j * FS + 8, third);
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      unsigned sb, sg, sr;
+      interp_sums(sh8, e.y, e.z, a0[j], a1[j], a2[j], b0[j], b1[j], b2[j], sb, sg, sr);
+      unsigned v = weight_pack<FULL>(sb, sg, sr, wm);
+      if (!FIRST) {
+        const unsigned old = lds32(aa + j * ACC_WORDS * 4);
+        v = nosat ? v + old : sat_add_bgr(v, old);                        // cv2.add chain, reference camera order
+      }
+      sts32(aa + j * ACC_WORDS * 4, v);
+    }
+  }
+}
+
+template <bool BAL, int NB, int FS, int STAGES>
+__global__ void __launch_bounds__(TMA_THREADS, BEVK_TMA_MIN_CTAS) k_bev_tma(const TmaParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // stages need 128-byte alignment for cp.async.bulk.tensor; align the base to 1024 (pointer arithmetic only, so the
+  // compiler keeps the shared address space)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned* acc = reinterpret_cast<unsigned*>(smem + (size_t)STAGES * NB * FS);   // [NB][ACC_WORDS] packed BGRX
+  const unsigned bar_full = smem_u32(acc + NB * ACC_WORDS), bar_empty = bar_full + 8 * STAGES;
+  const unsigned stage0 = smem_u32(smem), acc_u32 = smem_u32(acc);
+  __shared__ unsigned long long s_sum[BAL ? 3 * NB : 1];
+  const int t = threadIdx.x, lane = t & 31, wrp = t >> 5;
+  if (BAL && t < 3 * NB) s_sum[t] = 0ull;
+  if (t == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);                      // the producer's arrive.expect_tx
+      mbar_init(bar_empty + 8 * s, TMA_CONSUMERS / 32);    // one arrival per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int groups = (P.batch + NB - 1) / NB;
+  const long long n_units = (long long)P.n_tiles * groups;
+
+  if (t >= TMA_CONSUMERS) {
+    // ---------------- producer: one thread walks the same (unit, item) sequence and keeps the ring full
+    if (t == TMA_CONSUMERS) {
+      unsigned n = 0;
+      for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int tile_id = (int)(unit % P.n_tiles);
+        const int b0 = (int)(unit / P.n_tiles) * NB;
+        const int nb = min(NB, P.batch - b0);
+        const int4 tile = __ldg(P.tiles + tile_id);
+        for (int it = tile.z; it < tile.z + tile.w; ++it) {
+          const int4 i0 = __ldg(reinterpret_cast<const int4*>(P.items + it));
+          const int4 i1 = __ldg(reinterpret_cast<const int4*>(P.items + it) + 1);
+          const int cam = (short)(i0.y & 0xffff), flags = (i0.y >> 24) & 0xff;
+          if (cam < P.cam_lo || cam >= P.cam_hi || (flags & ITEM_GATHER)) continue;
+          const unsigned shape = (unsigned)i0.z >> 16;
+          const unsigned s = n % STAGES, ph = (n / STAGES) & 1u;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u);           // consumers have left this stage
+          mbar_expect_tx(bar_full + 8 * s, (unsigned)nb * (unsigned)i1.y);
+          const uint8_t* map = P.maps + (size_t)shape * TMA_DESC_BYTES;
+          for (int j = 0; j < nb; ++j)
+            tma_load_3d(stage0 + (s * NB + j) * FS, map, i0.w, i1.x, (b0 + j) * P.n_cam + cam, bar_full + 8 * s);
+          ++n;
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers
+  unsigned n = 0;
+  const int posx = wrp * ACC_WPITCH + lane, stepx = 8 * ACC_WPITCH;   // lanes along canvas x: line k*8+wrp is a row
+  const int posy = lane * ACC_WPITCH + wrp, stepy = 8;                // lanes along canvas y: line k*8+wrp is a column
+  for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const int tile_id = (int)(unit % P.n_tiles);
+    const int b0 = (int)(unit / P.n_tiles) * NB;
+    const int nb = min(NB, P.batch - b0);
+    const int4 tile = __ldg(P.tiles + tile_id);
+    consumer_sync();   // previous unit's write-out has read the accumulators
+    int first_cam = -1, prev_orient = -1;
+    for (int it = tile.z; it < tile.z + tile.w; ++it) {
+      const int4 i0 = __ldg(reinterpret_cast<const int4*>(P.items + it));
+      const int cam = (short)(i0.y & 0xffff), orient = (i0.y >> 16) & 0xff, flags = (i0.y >> 24) & 0xff;
+      if (cam < P.cam_lo || cam >= P.cam_hi) continue;
+      if (first_cam < 0) first_cam = cam;
+      const bool first = cam == first_cam;               // this camera stores, later ones add (cv2.add order)
+      if (prev_orient >= 0 && prev_orient != orient) consumer_sync();   // accumulator ownership changes with the orientation
+      prev_orient = orient;
+      const int k0 = i0.z & 0xff, k1 = (i0.z >> 8) & 0xff;
+      const bool nosat = (flags & ITEM_NOSAT) != 0;
+      const uint4* __restrict__ L = P.lut + (size_t)i0.x * (TILE * TILE) + t;
+      // shared address of this thread's accumulator word of group 0 / step to the next group, frame-set 0
+      const unsigned aa = acc_u32 + 4u * (unsigned)(orient ? posy : posx), astep = 4u * (unsigned)(orient ? stepy : stepx);
+      if (flags & ITEM_GATHER) {
+        // frame-set j of this unit and camera: frame0 + j * set_stride (the batch tail aliases frame-set b0: computed, never written)
+        const uint8_t* frame0 = P.base + (long long)(b0 * P.n_cam + cam) * P.frame_stride;
+        const long long set_stride = nb == NB ? (long long)P.n_cam * P.frame_stride : 0ll;
+        uint4 nxt = __ldg(L + k0 * 256);
+#pragma unroll 1
+        for (int k = k0; k < k1; ++k) {
+          const uint4 e = nxt;
+          if (k + 1 < k1) nxt = __ldg(L + (k + 1) * 256);
+          gather_entry<NB>(P, e, aa + k * astep, first, nosat, frame0, set_stride);
+        }
+      } else {
+        const unsigned s = n % STAGES, ph = (n / STAGES) & 1u;
+        const unsigned sbase = stage0 + s * NB * FS;
+        mbar_wait(bar_full + 8 * s, ph);                 // the boxes of all nb frame-sets have landed
+        if (!first) tma_item<NB, FS, false, false>(L, k0, k1, sbase, aa, astep, nosat);
+        else if (flags & ITEM_FULL) tma_item<NB, FS, true, true>(L, k0, k1, sbase, aa, astep, nosat);
+        else tma_item<NB, FS, true, false>(L, k0, k1, sbase, aa, astep, nosat);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * s);   // this warp no longer reads the stage
+        ++n;
+      }
+    }
+    const bool none = first_cam < 0;                      // tile without a camera (car hole): zeros
+    consumer_sync();
+    // ---- write the tile(s)
+    if (!BAL && tile.x + TILE <= P.BW && (P.BW & 3) == 0 && (P.canvas_bytes & 3) == 0) {
+      // interior tile: 32 rows x 24 words, written as 3 x 256 consecutive words (a warp store = two 96-byte row pieces)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int idx = i * 256 + t, r = idx / 24, w = idx - r * 24;
+        const int gy = tile.y + r;
+        if (gy >= P.BH) continue;
+        const size_t word_off = ((size_t)gy * P.BW * 3 + (size_t)tile.x * 3) / 4 + w;
+        const unsigned cw = P.car ? __ldg(reinterpret_cast<const unsigned*>(P.car) + word_off) : 0u;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          if (j >= nb) break;
+          unsigned v = none ? 0u : tile_row_word(acc + j * ACC_WORDS + r * ACC_WPITCH, w);
+          if (P.car) v = lane_addus4(v, cw);
+          reinterpret_cast<unsigned*>(P.out + (size_t)(b0 + j) * P.canvas_bytes)[word_off] = v;
+        }
+      }
+      continue;
+    }
+    // edge tiles and the BALANCE variant: thread t -> row t/8, 4 pixels (12 bytes) at pixel 4*(t%8)
+    const int row = t >> 3, chunk = t & 7;
+    const int gy = tile.y + row, gx = tile.x + chunk * 4;
+    const bool inb = (gy < P.BH) && (gx < P.BW);
+    const size_t pix_off = (size_t)gy * P.BW * 3 + (size_t)gx * 3;
+    const bool full = inb && (gx + 4 <= P.BW) && ((P.BW * 3) % 4 == 0) && (P.canvas_bytes % 4 == 0);
+    const int npx = inb ? min(4, P.BW - gx) : 0;
+    unsigned c0 = 0, c1 = 0, c2 = 0;
+    if (!BAL && P.car && full) {
+      const unsigned* c = reinterpret_cast<const unsigned*>(P.car + pix_off);
+      c0 = __ldg(c); c1 = __ldg(c + 1); c2 = __ldg(c + 2);
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      if (j >= nb) break;
+      const unsigned* a = acc + j * ACC_WORDS + row * ACC_WPITCH + chunk * 4;
+      unsigned x0 = a[0], x1 = a[1], x2 = a[2], x3 = a[3];                 // BGRX BGRX BGRX BGRX
+      if (none) x0 = x1 = x2 = x3 = 0u;
+      unsigned w0 = lane_perm(x0, x1, 0x4210);                             // B0 G0 R0 B1
+      unsigned w1 = lane_perm(x1, x2, 0x5421);                             // G1 R1 B2 G2
+      unsigned w2 = lane_perm(x2, x3, 0x6542);                             // R2 B3 G3 R3
+      if (BAL) {   // channel sums of the composed canvas, before gains and car (surroundBEV.py:44-47)
+        const unsigned px[4] = {x0, x1, x2, x3};
+        unsigned sb = 0, sg = 0, sr = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < npx) { sb += px[q] & 255u; sg += (px[q] >> 8) & 255u; sr += (px[q] >> 16) & 255u; }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {   // every lane takes part (out-of-canvas lanes add 0)
+          sb += __shfl_xor_sync(0xffffffffu, sb, s);
+          sg += __shfl_xor_sync(0xffffffffu, sg, s);
+          sr += __shfl_xor_sync(0xffffffffu, sr, s);
+        }
+        if (lane == 0) {
+          atomicAdd(&s_sum[3 * j + 0], (unsigned long long)sb);
+          atomicAdd(&s_sum[3 * j + 1], (unsigned long long)sg);
+          atomicAdd(&s_sum[3 * j + 2], (unsigned long long)sr);
+        }
+      }
+      if (!inb) continue;
+      uint8_t* o = P.out + (size_t)(b0 + j) * P.canvas_bytes + pix_off;
+      if (full) {
+        if (!BAL && P.car) { w0 = lane_addus4(w0, c0); w1 = lane_addus4(w1, c1); w2 = lane_addus4(w2, c2); }
+        unsigned* g = reinterpret_cast<unsigned*>(o);
+        g[0] = w0; g[1] = w1; g[2] = w2;
+      } else {
+        const unsigned wv[3] = {w0, w1, w2};
+#pragma unroll 1
+        for (int i = 0; i < npx * 3; ++i) {
+          int v = (wv[i >> 2] >> (8 * (i & 3))) & 255u;
+          if (!BAL && P.car) v = min(255, v + P.car[pix_off + i]);
+          o[i] = (uint8_t)v;
+        }
+      }
+    }
+    if (BAL) {
+      consumer_sync();
+      if (t < 3 * nb) { atomicAdd(P.csum + (size_t)(b0 + t / 3) * 3 + (t % 3), s_sum[t]); s_sum[t] = 0ull; }
+    }
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace bevk

@@ -155,32 +155,67 @@ def luminance_balance(images, ctx: L.Context | None = None):
 
 
 class Undistorter:
-    """Device-resident undistortion map (or fused camera model) + per-frame gather."""
-    _next_slot = 0
+    """Device-resident undistortion map (or fused camera model) + per-frame gather.
+
+    A bevk_ctx has 8 undistorter slots.  Each live Undistorter owns one slot of its ctx; the slot returns to the
+    pool on close() / garbage collection, and a 9th live object on one ctx raises instead of silently taking over a
+    slot another object still uses."""
 
     def __init__(self, K, D, P, size, model: str = "fisheye", fused: bool = False, ctx: L.Context | None = None,
                  slot: int | None = None):
         self.ctx = ctx or L.default_context()
+        self.slot = None
+        live = self.ctx.__dict__.setdefault("_und_slots", set())
         if slot is None:
-            slot = Undistorter._next_slot % 8
-            Undistorter._next_slot += 1
-        self.slot = slot
+            free = [i for i in range(8) if i not in live]
+            if not free and ctx is None:
+                # the shared default context is full (e.g. two BevGenerators' cameras): this object gets its own
+                self.ctx = L.Context(self.ctx.device)
+                live = self.ctx.__dict__.setdefault("_und_slots", set())
+                free = [0]
+            if not free:
+                raise L.BevkError("all 8 undistorter slots of this context are in use: close() an Undistorter "
+                                  "(or let it be collected), or give this one its own Context")
+            slot = free[0]
+        elif not 0 <= int(slot) < 8:
+            raise L.BevkError(f"slot {slot} out of range [0, 8)")
+        elif slot in live:
+            raise L.BevkError(f"undistorter slot {slot} of this context is owned by a live Undistorter")
         self.w, self.h = int(size[0]), int(size[1])
         d = np.asarray(D, np.float64).reshape(-1)
         m = L.MODEL_FISHEYE if model == "fisheye" else L.MODEL_PINHOLE
         L.check(self.ctx.lib.bevk_undistorter_set(self.ctx.h, slot, m, L.dptr(K), L.dptr(d), int(d.size), L.dptr(P),
                                                   self.w, self.h, int(fused)))
+        self.slot = int(slot)
+        live.add(self.slot)
+
+    def close(self):
+        if getattr(self, "slot", None) is not None:
+            self.ctx.__dict__.get("_und_slots", set()).discard(self.slot)
+            self.slot = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _live(self):
+        if self.slot is None:
+            raise L.BevkError("this Undistorter was closed")
 
     def maps(self):
+        self._live()
         m1 = np.empty((self.h, self.w, 2), np.int16)
         m2 = np.empty((self.h, self.w), np.uint16)
         L.check(self.ctx.lib.bevk_undistorter_maps(self.ctx.h, self.slot, L.vptr(m1), L.vptr(m2)))
         return m1, m2
 
     def __call__(self, src: np.ndarray, interpolation: int = INTER_LINEAR, out: np.ndarray | None = None) -> np.ndarray:
+        self._live()
         img, sw, sh, ss, ch = L.image_view(src)
         out = _out((self.h, self.w) if src.ndim == 2 else (self.h, self.w, ch), out)
-        L.check(self.ctx.lib.bevk_undistort(self.ctx.h, self.slot, L.vptr(img), sw, sh, ss, ch, L.vptr(out),
+        L.check(self.ctx.lib.bevk_undistort(self.ctx.h, self.slot, L.vptr(img), sw, sh, ss, ch, L.vptr(out), self.w, self.h,
                                             self.w * ch, _interp(interpolation)))
         return out
 
@@ -252,6 +287,8 @@ class BevEngine:
         if not self.finalized:
             self.finalize()
         batch = len(frame_sets)
+        if batch < 1:
+            raise L.BevkError("run() needs at least one frame-set")
         keep, ptrs, stride = [], (C.c_void_p * (batch * self.n_cam))(), None
         for b, fs in enumerate(frame_sets):
             if len(fs) != self.n_cam:
@@ -267,8 +304,7 @@ class BevEngine:
                         raise L.BevkError("all frames of a call must share one row stride")
                 keep.append(img)
                 ptrs[b * self.n_cam + k] = img.ctypes.data
-        if out is None:
-            out = np.empty((batch, self.BH, self.BW, 3), np.uint8)
+        out = _out((batch, self.BH, self.BW, 3), out)
         carp = None
         if car is not None:
             car = np.ascontiguousarray(car, np.uint8)
@@ -292,9 +328,10 @@ class BevEngine:
         return int(self.ctx.lib.bevk_bev_last_h2d_bytes(self.ctx.h))
 
     def _conform(self, f: np.ndarray) -> np.ndarray:
-        """The reference never validates frame sizes (cv2.remap samples whatever it is given,
-        zero outside).  The engine's LUT is compiled for FW x FH, so other sizes are embedded
-        into / cropped to an FW x FH zero canvas, which samples identically."""
+        """The reference never validates frame sizes (cv2.remap samples whatever it is given, zero outside).  The engine's
+        LUT is compiled for FW x FH: a SMALLER frame is embedded into an FW x FH zero canvas, which samples identically
+        (cv2's BORDER_CONSTANT 0).  A LARGER frame is cropped, which differs from the reference wherever the LUT points
+        beyond FW x FH (the reference would sample the extra pixels there, this engine reads zeros)."""
         if f.ndim != 3 or f.shape[2] != 3 or f.dtype != np.uint8:
             raise L.BevkError("frames must be uint8[h][w][3] (BGR)")
         if f.shape[0] == self.FH and f.shape[1] == self.FW:
@@ -310,6 +347,29 @@ class BevEngine:
             self.finalize()
         L.check(self.ctx.lib.bevk_bev_run_device(self.ctx.h, C.c_void_p(d_srcs_ptr), batch, C.c_void_p(d_car_ptr or None),
                                                  L.FLAG_BALANCE if balance else 0, C.c_void_p(d_out_ptr)))
+
+    def run_stack(self, d_frames_ptr: int, frame_stride: int, batch: int, d_out_ptr: int, d_car_ptr: int = 0, balance: bool = False):
+        """Frame stack on the device (frame i at d_frames_ptr + i * frame_stride, i = set * n_cam + camera): the
+        TMA-staged kernel when base and stride are 16-byte aligned.  Only enqueues on the ctx stream."""
+        if not self.finalized:
+            self.finalize()
+        L.check(self.ctx.lib.bevk_bev_run_stack(self.ctx.h, C.c_void_p(d_frames_ptr), int(frame_stride), batch,
+                                                C.c_void_p(d_car_ptr or None), L.FLAG_BALANCE if balance else 0, C.c_void_p(d_out_ptr)))
+
+    def run_stack_cams(self, d_frames_ptr: int, frame_stride: int, batch: int, cam_lo: int, cam_hi: int, d_out_ptr: int):
+        if not self.finalized:
+            self.finalize()
+        L.check(self.ctx.lib.bevk_bev_run_stack_cams(self.ctx.h, C.c_void_p(d_frames_ptr), int(frame_stride), batch, cam_lo,
+                                                     cam_hi, C.c_void_p(d_out_ptr)))
+
+    def last_path(self) -> str:
+        """Which fused kernel the last call launched: 'tma' (k_bev_tma) or 'gather' (k_bev)."""
+        return {1: "gather", 2: "tma"}.get(int(self.ctx.lib.bevk_bev_last_path(self.ctx.h)), "none")
+
+    def tma_plan_info(self):
+        v = [C.c_int64() for _ in range(5)]
+        L.check(self.ctx.lib.bevk_bev_tma_plan_info(self.ctx.h, *[C.byref(x) for x in v]))
+        return dict(zip(("items", "shapes", "box_bytes", "tma_entries", "gather_entries"), (x.value for x in v)))
 
     def run_cuda(self, frames, car=None, balance: bool = False, out=None, stream: int | None = None):
         """Frames that already live on the GPU (decoder output, torch / CuPy arrays): no PCIe in the call.

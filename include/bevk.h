@@ -53,6 +53,9 @@ int bevk_ctx_destroy(bevk_ctx *ctx);
  * restores the ctx's own stream. */
 int bevk_ctx_set_stream(bevk_ctx *ctx, void *cuda_stream);
 int bevk_ctx_sync(bevk_ctx *ctx);
+/* PCI bus id ("0000:1b:00.0") of a CUDA device: lets a multi-process launcher bind each rank to the CPUs and memory
+ * of its GPU's NUMA node (/sys/bus/pci/devices/<id>/local_cpulist) before it allocates page-locked buffers. */
+int bevk_device_pci_bus_id(int device, char *out, int len);
 /* Pinned host memory for callers who want full-rate PCIe copies. */
 int bevk_host_alloc(uint64_t bytes, void **out);
 int bevk_host_free(void *p);
@@ -82,8 +85,10 @@ int bevk_remap(bevk_ctx *ctx, const uint8_t *src, int sw, int sh, int64_t sstrid
 int bevk_undistorter_set(bevk_ctx *ctx, int slot, int model, const double K[9], const double *D, int n_dist,
                          const double P[9], int dw, int dh, int fused);
 int bevk_undistorter_maps(bevk_ctx *ctx, int slot, int16_t *map1, uint16_t *map2);   /* D2H, for parity tests */
+/* dw x dh: the destination size the caller allocated; must equal the slot's map size (checked, so a stale handle to
+ * a slot that was re-set can never make the library write past dst). */
 int bevk_undistort(bevk_ctx *ctx, int slot, const uint8_t *src, int sw, int sh, int64_t sstride, int channels,
-                   uint8_t *dst, int64_t dstride, int interp);
+                   uint8_t *dst, int dw, int dh, int64_t dstride, int interp);
 
 /* ---- K4: cv2.warpPerspective(src, H, (dw,dh), flags=interp), border 0 --------
  *   ExtrinsicCalibration/extrinsicCalib.py:166-169, surroundBEV.py:113-114      */
@@ -136,10 +141,22 @@ int bevk_bev_run_device(bevk_ctx *ctx, const void *d_srcs, int batch, const void
  * copy per call.  Replaces the host frames of BevGenerator.__call__ (surroundBEV.py:312-325) when the
  * decoder already left them on the GPU.  Only enqueues on the ctx stream.             */
 int bevk_bev_run_frames(bevk_ctx *ctx, const void *const *frames, int batch, const void *d_car, int flags, void *d_out);
+/* Frame STACK on the device: frame i (= frame-set i / n_cam, camera i % n_cam) is the dense uint8[frame_h][frame_w][3]
+ * at d_frames + i * frame_stride -- e.g. one uint8[batch][n_cam][H][W][3] tensor, or a decoder's surface pool.
+ * Replaces the frames of BevGenerator.__call__ (surroundBEV.py:312-325, the cv2.remap inputs of :116-117).  With a
+ * 16-byte aligned base and stride (and a row pitch frame_w*3 that is a multiple of 16) the TMA-staged kernel runs:
+ * per (canvas tile, camera) one cp.async.bulk.tensor box per frame-set into shared memory; otherwise the
+ * pointer-table gather.  bevk_bev_run_frames takes this path by itself when its table describes a stack, and so
+ * does bevk_bev_run for its staging buffers.  Only enqueues on the ctx stream.                           */
+int bevk_bev_run_stack(bevk_ctx *ctx, const void *d_frames, int64_t frame_stride, int batch, const void *d_car, int flags,
+                       void *d_out);
 /* Per-camera partial canvases for camera-sharded multi-GPU runs: rank r renders only
  * cameras [cam_lo, cam_hi) into d_out (zero elsewhere); the saturating sum of the
  * ranks' partials equals the full canvas (balance is not supported in this mode). */
 int bevk_bev_run_device_cams(bevk_ctx *ctx, const void *d_srcs, int batch, int cam_lo, int cam_hi, void *d_out);
+/* The same over a frame stack (see bevk_bev_run_stack). */
+int bevk_bev_run_stack_cams(bevk_ctx *ctx, const void *d_frames, int64_t frame_stride, int batch, int cam_lo, int cam_hi,
+                            void *d_out);
 /* Saturating sum of n partial canvases (device), optional car, into d_out. */
 int bevk_sat_sum_device(bevk_ctx *ctx, const void *const *d_parts_host_array, int n, uint64_t bytes,
                         const void *d_car, void *d_out);
@@ -162,6 +179,24 @@ int bevk_bev_host_copy_bytes(bevk_ctx *ctx, int flags, int64_t *h2d_per_frame_se
 /* Host->device bytes the last bevk_bev_run call actually moved (page-locked frames are ingested span
  * by span by the SMs, pageable ones by DMA rectangles, BALANCE uploads whole frames). */
 int64_t bevk_bev_last_h2d_bytes(bevk_ctx *ctx);
+/* Which fused kernel the last BEV call launched: 1 = k_bev (pointer-table gather), 2 = k_bev_tma (TMA-staged). */
+int bevk_bev_last_path(bevk_ctx *ctx);
+/* The TMA-staged kernel's plan: work items, tensor-map box shapes, bytes one frame-set's boxes deliver, LUT entries
+ * served from staged boxes / by global gathers.  All zero when the plan does not exist (row pitch not a multiple of
+ * 16 bytes, or BEVK_TMA=0). */
+int bevk_bev_tma_plan_info(bevk_ctx *ctx, int64_t *n_items, int64_t *n_shapes, int64_t *box_bytes, int64_t *tma_entries,
+                           int64_t *gather_entries);
+/* ---- CUDA graphs over the device-pointer entry points ------------------------------------------------
+ * Everything the "_device" / "_stack" / "_frames" entry points enqueue on the ctx stream between begin and end is
+ * captured (stream capture) instead of executed, instantiated once, and replayed `times` times by one call --
+ * BevGenerator.__call__ (surroundBEV.py:312-325) for a fixed set of device buffers costs one graph launch per
+ * frame-set instead of up to five kernel launches and two memsets (BALANCE), and a host that stalls between calls
+ * cannot starve the GPU.  Run the same calls once before capturing: a call that has to allocate or build tables
+ * inside a capture fails, and bevk_graph_end reports it.  Host-pointer entry points cannot be captured.       */
+int bevk_graph_begin(bevk_ctx *ctx);
+int bevk_graph_end(bevk_ctx *ctx, int *graph_id);
+int bevk_graph_launch(bevk_ctx *ctx, int graph_id, int times);
+int bevk_graph_destroy(bevk_ctx *ctx, int graph_id);
 /* Kernel launches issued by this ctx since creation (bench "gpu_launches"). */
 int64_t bevk_launch_count(bevk_ctx *ctx);
 /* Milliseconds spent in the last bevk_bev_run_device call's kernels, measured with

@@ -14,6 +14,7 @@
 #include "../../cameracalibration_b200/csrc/bevk_bev.cuh"
 #include "../../cameracalibration_b200/csrc/bevk_kernels.cuh"
 #include "../../cameracalibration_b200/csrc/bevk_plan.cuh"
+#include "../../cameracalibration_b200/csrc/bevk_plan_tma.cuh"
 #include "../../cameracalibration_b200/csrc/bevk_gather4.cuh"
 
 using namespace bevk;
@@ -215,7 +216,7 @@ static int mode_balance() {
 // BALANCE sequence (V sums, offsets, balanced row spans, gather, channel sums, gains, car), without threads.
 // in.bin : int32 NC FW FH BW BH nearest balance has_car; per camera map1 int16[BH*BW*2], map2 uint16[BH*BW],
 //          mask u8[BH*BW]; NC frames u8[FH*FW*3]; car u8[BH*BW*3] if has_car.   out.bin: canvas u8[BH*BW*3]
-static int mode_bev(const char* in_path, const char* out_path) {
+static int mode_bev(const char* in_path, const char* out_path, int tma_stage_bytes /* 0: round-1 gather plan */) {
   FILE* f = fopen(in_path, "rb");
   if (!f) return 5;
   int hd[8];
@@ -270,9 +271,77 @@ static int mode_bev(const char* in_path, const char* out_path) {
         }
       }
   }
-  // ---- the gather (k_bev)
-  const SlowGeo geo = {(unsigned)FW * 3u, FW, FH};
   std::vector<uint8_t> canvas(npx * 3, 0);
+  const SlowGeo geo = {(unsigned)FW * 3u, FW, FH};
+  if (tma_stage_bytes > 0) {
+    // ---- k_bev_tma: the TMA plan, boxes modelled as the copy delivers them (zero outside the frame)
+    TmaPlan tp;
+    {
+      std::vector<const short*> p1(NC);
+      std::vector<const unsigned short*> p2(NC);
+      std::vector<const uint8_t*> pm(NC);
+      for (int k = 0; k < NC; ++k) { p1[k] = m1[k].data(); p2[k] = m2[k].data(); pm[k] = mk[k].data(); }
+      build_tma_plan(NC, FW, FH, BW, BH, nearest != 0, p1.data(), p2.data(), pm.data(), tma_stage_bytes, true, tp);
+    }
+    std::vector<uint8_t> stage((size_t)tma_stage_bytes + 16, 0xEE);
+    for (const int4& tile : tp.tiles) {
+      unsigned acc[ACC_WORDS];
+      for (auto& a : acc) a = 0xdeadbeefu;                 // every word must be written before the write-out reads it
+      int first_cam = -1;
+      for (int it = tile.z; it < tile.z + tile.w; ++it) {
+        const TmaItem item = tp.items[it];
+        if (first_cam < 0) first_cam = item.cam;
+        const bool first = item.cam == first_cam, nosat = (item.flags & ITEM_NOSAT) != 0, gather = (item.flags & ITEM_GATHER) != 0;
+        const uint8_t* src = (balance ? bal : frames)[item.cam].data();
+        if (!gather) {
+          memset(stage.data(), 0xEE, stage.size());
+          const int2 shape = tp.shapes[item.shape];
+          CHECK((unsigned)(shape.x * 4 * shape.y) == item.tx_bytes && (int)item.tx_bytes <= tma_stage_bytes, "box bytes");
+          CHECK((item.xw & 3) == 0 && (shape.x & 3) == 0, "box alignment");
+          model_tma_box(src, FW, FH, shape, item.xw, item.y, stage.data());
+        }
+        for (int k = item.k0; k < item.k1; ++k)
+          for (int t = 0; t < 256; ++t) {
+            const int lane = t & 31, wrp = t >> 5;
+            const int pos = item.orient ? lane * ACC_WPITCH + wrp : wrp * ACC_WPITCH + lane;
+            const int step = item.orient ? 8 : 8 * ACC_WPITCH;
+            const uint4 e = tp.lut[(size_t)item.lut_block * (TILE * TILE) + k * 256 + t];
+            unsigned* a = acc + pos + k * step;
+            if (!(e.w & T_ACTIVE)) { if (first) *a = 0u; continue; }
+            unsigned v;
+            if (gather && (e.w & T_SLOW)) {
+              v = sample_slow_core(geo, src, e.x, (e.w & 0x1ffffu) | (((e.w >> 19) & 1023u) << 17));
+            } else {
+              const unsigned sh8 = (e.w >> 14) & 24u, wm = e.w & 0x1ffffu;
+              const bool third = sh8 == 24u;
+              const uint8_t *q0, *q1;
+              if (gather) { q0 = src + (e.x & ~3u); q1 = q0 + geo.pitch; }
+              else {
+                q0 = stage.data() + (e.x & 0xffffu); q1 = stage.data() + (e.x >> 16);
+                CHECK((e.x >> 16) + (third ? 12u : 8u) <= item.tx_bytes, "entry reads past its box");
+              }
+              unsigned sb, sg, sr;
+              interp_sums(sh8, e.y, e.z, ldg32(q0), ldg32(q0 + 4), third ? ldg32(q0 + 8) : 0u, ldg32(q1), ldg32(q1 + 4),
+                          third ? ldg32(q1 + 8) : 0u, sb, sg, sr);
+              v = (item.flags & ITEM_FULL) && !gather ? weight_pack<true>(sb, sg, sr, wm) : weight_pack<false>(sb, sg, sr, wm);
+            }
+            *a = first ? v : (nosat ? v + *a : sat_add_bgr(v, *a));
+          }
+      }
+      for (int row = 0; row < TILE; ++row)
+        for (int col = 0; col < TILE; ++col) {
+          const int gx = tile.x + col, gy = tile.y + row;
+          if (gx >= BW || gy >= BH) continue;
+          const unsigned px = first_cam < 0 ? 0u : acc[row * ACC_WPITCH + col];
+          CHECK(first_cam < 0 || (px >> 24) == 0, "accumulator word not written or carried into byte 3");
+          uint8_t* o = canvas.data() + ((size_t)gy * BW + gx) * 3;
+          o[0] = px & 255u; o[1] = (px >> 8) & 255u; o[2] = (px >> 16) & 255u;
+        }
+    }
+    printf("tma plan: tiles=%zu items=%zu shapes=%zu box_bytes=%lld tma_entries=%lld gather_entries=%lld\n", tp.tiles.size(),
+           tp.items.size(), tp.shapes.size(), tp.box_bytes, tp.tma_entries, tp.gather_entries);
+  } else {
+  // ---- the gather (k_bev)
   for (const int4& tile : plan.tiles) {
     unsigned acc[ACC_WORDS];
     bool first = true;
@@ -310,6 +379,7 @@ static int mode_bev(const char* in_path, const char* out_path) {
         uint8_t* o = canvas.data() + ((size_t)gy * BW + gx) * 3;
         o[0] = px & 255u; o[1] = (px >> 8) & 255u; o[2] = (px >> 16) & 255u;
       }
+  }
   }
   // ---- BALANCE, part 2 (channel sums in k_bev<true>, k_gain) and the car overlay
   if (balance) {
@@ -392,7 +462,8 @@ static int mode_gather(int mode, int sw, int sh, int dw, int dh, const char* in_
 int main(int argc, char** argv) {
   if (argc == 9 && !strcmp(argv[1], "gather"))
     return mode_gather(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argv[7], argv[8]);
-  if (argc == 4 && !strcmp(argv[1], "bev")) return mode_bev(argv[2], argv[3]);
+  if (argc == 4 && !strcmp(argv[1], "bev")) return mode_bev(argv[2], argv[3], 0);
+  if (argc == 5 && !strcmp(argv[1], "bevtma")) { const int r = mode_bev(argv[2], argv[3], atoi(argv[4])); return r ? r : (fails ? 1 : 0); }
   if (argc == 2 && !strcmp(argv[1], "balance")) return mode_balance();
   if (argc == 6 && !strcmp(argv[1], "blend")) return mode_blend(atoi(argv[2]), atoi(argv[3]), argv[4], argv[5]);
   if (argc == 7 && !strcmp(argv[1], "bevmaps")) return mode_bevmaps(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argv[6]);

@@ -218,7 +218,18 @@ def _bev_on_host(exe, tmp_path, fx, g, calib, masks, frames, car, balance, neare
     r = subprocess.run([exe, "bev", str(tmp_path / "bev_in.bin"), str(tmp_path / "bev_out.bin")], capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
-    return np.fromfile(tmp_path / "bev_out.bin", np.uint8).reshape(g.BH, g.BW, 3), r.stdout
+    out = np.fromfile(tmp_path / "bev_out.bin", np.uint8).reshape(g.BH, g.BW, 3)
+    # the TMA-staged kernel's plan (bevk_plan_tma.cuh) through its own interpreter: boxes modelled as the tensor copy
+    # delivers them (zeros outside the frame), two stage sizes (the second forces strip splits and GATHER items)
+    info = r.stdout
+    for stage in (6144, 1536):
+        rt = subprocess.run([exe, "bevtma", str(tmp_path / "bev_in.bin"), str(tmp_path / "bevtma_out.bin"), str(stage)],
+                            capture_output=True, text=True, timeout=600)
+        assert rt.returncode == 0, (rt.returncode, rt.stdout, rt.stderr)
+        out_t = np.fromfile(tmp_path / "bevtma_out.bin", np.uint8).reshape(g.BH, g.BW, 3)
+        assert (out_t == out).all(), (stage, int((out_t != out).sum()), rt.stdout)
+        info += rt.stdout
+    return out, info
 
 
 @pytest.mark.parametrize("blend", [False, True])
