@@ -245,7 +245,8 @@ def main():
     config = {"workload": f"{w['batch']} frame-sets/GPU x 4 cams {w['FW']}x{w['FH']} BGR -> {w['BW']}x{w['BH']} BEV, "
                           f"blend={w['blend']} balance={w['balance']} (BASELINE {a.workload} shape)",
               "sharding": ("frame-sets per GPU, no data-path collective" if a.shard == "frames" else
-                           "cameras per GPU, one NCCL all-gather of partial canvases per step + local saturating-sum compose"),
+                           "cameras per GPU: each rank renders its cameras' slabs (tile-aligned mask bounding boxes), ONE "
+                           "ncclAllGather of the slabs per step over NVLink, local saturating compose; every rank ends with all canvases"),
               "launch": "one step captured as a CUDA graph, the K timed steps replayed by one bevk_graph_launch call",
               "l2": f"inputs ({w['batch'] * 4 * w['FW'] * w['FH'] * 3 / 1e6:.0f} MB/step) larger than L2; "
                     "the frame-invariant LUT stays L2-resident by design"}
@@ -328,9 +329,11 @@ def main():
     use_table = bool(os.environ.get("BEVK_BENCH_TABLE"))   # A/B switch: frames through a device pointer table (round-1 gather kernel)
 
     def step():
-        if cams or use_table:
-            with torch.cuda.stream(stream):   # NCCL orders itself against torch's current stream
-                sharded.render(ptrs, nb, d_out, None, balance=w["balance"])
+        if cams:
+            # one camera block per rank: slabs -> ONE ncclAllGather -> compose, all on `stream` (bevk_bev_run_sharded)
+            sharded.render(d_frames, d_out, None, w["balance"], stream=stream.cuda_stream)
+        elif use_table:
+            eng.run_device(ptrs.data_ptr(), nb, d_out.data_ptr(), 0, w["balance"])
         else:
             # the batch is one uint8[batch][cam][FH][FW][3] tensor = a frame stack: TMA-staged kernel
             eng.run_stack(d_frames.data_ptr(), fbytes, nb, d_out.data_ptr(), 0, w["balance"])
@@ -478,6 +481,7 @@ def main():
                              "kernel_ms_isolated": k_ms, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg,
                              "algorithmic_bytes_per_frame_set": {"source_unique_32B_sectors": src_b, "canvas_write": canvas_b}},
+                "link_bytes_per_step": sharded.link_bytes() if cams else 0,
                 "clocks": sampler.summary(), "plan": dict(eng.plan_info(), tma=eng.tma_plan_info(), path=path_used)}
         if not a.no_cpu_baseline and world == 1:
             v, cores, sample = cpu_reference(w, calib, masks, n_sets=4, repeats=100000, seconds_cap=20.0)

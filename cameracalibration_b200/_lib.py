@@ -15,6 +15,7 @@ INTER_NEAREST, INTER_LINEAR = 0, 1
 MAPS_UNDISTORT, MAPS_BEV = 0, 1
 MODEL_FISHEYE, MODEL_PINHOLE = 0, 1
 FLAG_BALANCE = 1
+SHARD_FRAMES, SHARD_CAMERAS = 0, 1
 MAX_CAMERAS = 8
 
 _p = C.c_void_p
@@ -60,6 +61,14 @@ SIGNATURES = {
     "bevk_bev_last_h2d_bytes": (C.c_int64, [_p]),
     "bevk_bev_last_path": (C.c_int, [_p]),
     "bevk_bev_tma_plan_info": (C.c_int, [_p] + [C.POINTER(C.c_int64)] * 5),
+    "bevk_shard_configure": (C.c_int, [_p, C.c_int, C.c_int, C.c_int]),
+    "bevk_shard_unique_id": (C.c_int, [_p, C.c_int]),
+    "bevk_shard_connect": (C.c_int, [_p, _p, C.c_int]),
+    "bevk_shard_info": (C.c_int, [_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "bevk_bev_run_sharded": (C.c_int, [_p, _p, C.c_int64, C.c_int, _p, C.c_int, _p]),
+    "bevk_shard_last_link_bytes": (C.c_int64, [_p]),
+    "bevk_shard_render": (C.c_int, [_p, _p, C.c_int64, C.c_int, C.c_int, _p]),
+    "bevk_shard_compose": (C.c_int, [_p, _p, C.c_int, _p, _p]),
     "bevk_graph_begin": (C.c_int, [_p]),
     "bevk_graph_end": (C.c_int, [_p, C.POINTER(C.c_int)]),
     "bevk_graph_launch": (C.c_int, [_p, C.c_int, C.c_int]),
@@ -135,6 +144,7 @@ class Context:
         check(self.lib.bevk_ctx_create(int(device), C.byref(h)))
         self.h = h
         self.device = device
+        self._stream = None
 
     def close(self):
         if getattr(self, "h", None):
@@ -147,6 +157,8 @@ class Context:
         except Exception:
             pass
 
+    _UNSET = object()
+
     def set_stream(self, stream_ptr: int | None):
         """None -> the ctx's own stream; 0 (torch's default stream handle) -> the legacy
         default stream (cudaStreamLegacy); anything else -> that cudaStream_t."""
@@ -155,6 +167,12 @@ class Context:
         else:
             ptr = 1 if stream_ptr == 0 else stream_ptr
         check(self.lib.bevk_ctx_set_stream(self.h, _p(ptr)))
+        self._stream = stream_ptr
+
+    def on_stream(self, stream_ptr: int | None):
+        """``with ctx.on_stream(s): ...`` -- run the calls inside on stream ``s`` (same values as set_stream) and put
+        the previous stream back afterwards."""
+        return _StreamScope(self, stream_ptr)
 
     def sync(self):
         check(self.lib.bevk_ctx_sync(self.h))
@@ -167,6 +185,22 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self.lib.bevk_launch_count(self.h))
+
+
+class _StreamScope:
+    def __init__(self, ctx, stream_ptr):
+        self.ctx, self.want = ctx, stream_ptr
+
+    def __enter__(self):
+        self.prev = getattr(self.ctx, "_stream", None)
+        if self.want != self.prev:
+            self.ctx.set_stream(self.want)
+        return self.ctx
+
+    def __exit__(self, et, ev, tb):
+        if self.want != self.prev:
+            self.ctx.set_stream(self.prev)
+        return False
 
 
 class _GraphCapture:

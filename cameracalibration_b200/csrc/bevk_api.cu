@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
@@ -22,15 +23,22 @@
 #include "bevk_plan.cuh"
 #include "bevk_bev_tma.cuh"
 #include "bevk_plan_tma.cuh"
+#include "bevk_shard.cuh"
+
+#include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges cost nothing unless a profiler injects itself
 
 using namespace bevk;
 
-#ifndef BEVK_TMA_FS
-#define BEVK_TMA_FS 6144        // bytes of one frame-set's staged source box (plan: larger boxes split / gather)
-#endif
-#ifndef BEVK_TMA_STAGES
-#define BEVK_TMA_STAGES 2
-#endif
+// k_bev_tma configurations built into the library: FS = bytes of one frame-set's staged source box (a ring slot is 4 FS),
+// STAGES = ring slots, MINCTAS = resident CTAs per SM the register budget is set for.  The first entry is the default;
+// BEVK_TMA_CFG="<FS>,<STAGES>" (read at bevk_bev_finalize) selects another one for tuning runs.
+#define BEVK_TMA_CONFIGS(X) X(6144, 3, 2) X(6144, 2, 3) X(4096, 3, 3) X(4096, 4, 2) X(8192, 2, 2)
+struct TmaConfig { int fs, stages, min_ctas; };
+#define X(FS, ST, MC) {FS, ST, MC},
+static const TmaConfig kTmaConfigs[] = {BEVK_TMA_CONFIGS(X)};
+#undef X
+static const int kNumTmaConfigs = (int)(sizeof kTmaConfigs / sizeof kTmaConfigs[0]);
 
 
 // ------------------------------------------------------------------ errors
@@ -56,6 +64,12 @@ static int fail(int code, const char* fmt, ...) {
     int r_ = (call);          \
     if (r_ != BEVK_OK) return r_; \
   } while (0)
+
+// NVTX range for the lifetime of a scope (visible in nsys / ncu timelines: ingest, render, read-back)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ------------------------------------------------------------------ small helpers
 struct DevBuf {
@@ -112,7 +126,7 @@ struct BevCam {
 struct bevk_ctx {
   int device = 0;
   cudaStream_t own = nullptr, stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_switch = nullptr;
   cudaStream_t copy_stream = nullptr;                      // H2D side of the host-pointer pipeline
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   const void* ptrs_for = nullptr; const void* ptrs_tab = nullptr; long long ptrs_n = 0; size_t ptrs_pad = 0;   // cached frame pointer table
@@ -151,10 +165,22 @@ struct bevk_ctx {
   struct MapSet { const void* base = nullptr; long long stride = 0, frames = 0; DevBuf d; unsigned long long used = 0; };
   MapSet maps[4];
   unsigned long long map_clock = 0;
-  int tma_grid[4] = {0, 0, 0, 0};           // resident CTAs of k_bev_tma<BAL, NB>: index = 2*BAL + {NB=1:0, 4:1}
+  int tma_cfg = 0;                          // index into kTmaConfigs
+  int tma_grid[8][4] = {};                  // [config] resident CTAs of k_bev_tma<BAL, NB>: index = 2*BAL + {NB=1:0, 4:1}
   DevBuf d_stack_ptrs;                      // pointer table of a frame stack (BALANCE pre-passes read frames through a table)
   const void* stack_ptrs_base = nullptr; long long stack_ptrs_stride = 0, stack_ptrs_n = 0;
   int last_path = 0;                        // 1: k_bev (pointer-table gather), 2: k_bev_tma
+  // multi-GPU sharding (bevk_shard_*): partition, slab geometry, NCCL communicator
+  struct Shard {
+    bool configured = false, geometry = false;
+    int policy = 0, rank = 0, world = 1;
+    int cam_lo[SHARD_MAX_RANKS] = {}, cam_hi[SHARD_MAX_RANKS] = {};
+    SlabRect rect[SHARD_MAX_RANKS] = {};
+    long long slab_bytes = 0;
+    void* comm = nullptr;                   // ncclComm_t
+    DevBuf d_slabs;
+    long long last_link_bytes = 0;
+  } shard;
   // CUDA graphs captured from the device-pointer entry points (bevk_graph_*)
   bool capturing = false;
   long long capture_launches0 = 0;
@@ -203,6 +229,8 @@ int bevk_ctx_create(int device, bevk_ctx** out) {
   return BEVK_OK;
 }
 
+static void shard_release(bevk_ctx* c);
+
 int bevk_ctx_destroy(bevk_ctx* c) {
   if (!c) return BEVK_OK;
   cudaSetDevice(c->device);
@@ -213,11 +241,13 @@ int bevk_ctx_destroy(bevk_ctx* c) {
                     &c->d_stack_ptrs})
     b->release();
   for (auto& m : c->maps) m.d.release();
+  shard_release(c);
   for (auto& g : c->graphs) { if (g.x) cudaGraphExecDestroy(g.x); if (g.g) cudaGraphDestroy(g.g); }
   for (auto& u : c->und) { u.map1.release(); u.map2.release(); }
   for (auto& k : c->cam) { k.map1.release(); k.map2.release(); }
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
+  if (c->ev_switch) cudaEventDestroy(c->ev_switch);
   if (c->copy_stream) {
     cudaStreamSynchronize(c->copy_stream);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_free[i]); cudaEventDestroy(c->ev_hp[i]); }
@@ -233,10 +263,13 @@ int bevk_ctx_destroy(bevk_ctx* c) {
 int bevk_ctx_set_stream(bevk_ctx* c, void* s) {
   RET(use(c));
   cudaStream_t next = s ? reinterpret_cast<cudaStream_t>(s) : c->own;
-  if (next != c->stream && !c->user_tab.empty()) {   // the cached frame table of bevk_bev_run_frames is ordered on the old stream
-    CU(cudaStreamSynchronize(c->stream));
-    c->user_tab.clear();
-  }
+  if (next == c->stream) return BEVK_OK;
+  if (c->capturing) return fail(BEVK_ERR_ARG, "cannot change the stream inside a graph capture");
+  // Everything this ctx enqueued so far (kernels that read its cached tables, uploads that wrote them) is ordered before
+  // whatever it enqueues on the new stream: no host synchronisation, no table is dropped.
+  if (!c->ev_switch) CU(cudaEventCreateWithFlags(&c->ev_switch, cudaEventDisableTiming));
+  if (cudaEventRecord(c->ev_switch, c->stream) == cudaSuccess) CU(cudaStreamWaitEvent(next, c->ev_switch, 0));
+  else cudaGetLastError();   // the old (caller-owned) stream is gone: nothing of it can still be running
   c->stream = next;
   return BEVK_OK;
 }
@@ -566,6 +599,19 @@ int bevk_blend_masks(bevk_ctx* c, const uint8_t* polys, const int32_t* lines, in
   return BEVK_OK;
 }
 
+// the four instantiations of one k_bev_tma configuration: {BAL=0,NB=1}, {0,4}, {1,1}, {1,4}
+struct TmaFns { const void* fn[4]; };
+static TmaFns tma_fns(int cfg) {
+  int i = 0;
+#define X(FS, ST, MC)                                                                                            \
+  if (i++ == cfg)                                                                                                \
+    return TmaFns{{(const void*)k_bev_tma<false, 1, FS, ST, MC>, (const void*)k_bev_tma<false, 4, FS, ST, MC>,     \
+                   (const void*)k_bev_tma<true, 1, FS, ST, MC>, (const void*)k_bev_tma<true, 4, FS, ST, MC>}};
+  BEVK_TMA_CONFIGS(X)
+#undef X
+  return TmaFns{{nullptr, nullptr, nullptr, nullptr}};
+}
+
 // Tile-plan compiler: LUT maps + masks -> per-tile item lists and thread-ordered LUT blocks.
 int bevk_bev_finalize(bevk_ctx* c) {
   RET(use(c));
@@ -635,7 +681,14 @@ int bevk_bev_finalize(bevk_ctx* c) {
   CU(cudaStreamSynchronize(c->stream));
   // ---- the TMA-staged kernel's plan (frames whose row pitch is a multiple of 16 bytes)
   c->tma_planned = false;
-  c->tma_stage_bytes = BEVK_TMA_FS;
+  c->tma_cfg = 0;
+  if (const char* env = getenv("BEVK_TMA_CFG")) {
+    int fs = 0, st = 0;
+    if (sscanf(env, "%d,%d", &fs, &st) == 2)
+      for (int i = 0; i < kNumTmaConfigs; ++i)
+        if (kTmaConfigs[i].fs == fs && kTmaConfigs[i].stages == st) c->tma_cfg = i;
+  }
+  c->tma_stage_bytes = kTmaConfigs[c->tma_cfg].fs;
   {
     TmaPlan tp;
     std::vector<const short*> p1(NC);
@@ -662,18 +715,17 @@ int bevk_bev_finalize(bevk_ctx* c) {
       c->tma_planned = true;
     }
   }
-  if (c->tma_planned && c->tma_grid[0] == 0) {
+  if (c->tma_planned && c->tma_grid[c->tma_cfg][0] == 0) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, c->device));
-    const void* fn[4] = {(const void*)k_bev_tma<false, 1, BEVK_TMA_FS, BEVK_TMA_STAGES>, (const void*)k_bev_tma<false, 4, BEVK_TMA_FS, BEVK_TMA_STAGES>,
-                         (const void*)k_bev_tma<true, 1, BEVK_TMA_FS, BEVK_TMA_STAGES>, (const void*)k_bev_tma<true, 4, BEVK_TMA_FS, BEVK_TMA_STAGES>};
+    const TmaFns f = tma_fns(c->tma_cfg);
     const int nb[4] = {1, 4, 1, 4};
     for (int i = 0; i < 4; ++i) {
       int per_sm = 0;
-      const size_t smem = bev_tma_smem_bytes(nb[i], BEVK_TMA_FS, BEVK_TMA_STAGES);
-      CU(cudaFuncSetAttribute(fn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn[i], TMA_THREADS, smem));
-      c->tma_grid[i] = std::max(1, per_sm) * prop.multiProcessorCount;
+      const size_t smem = bev_tma_smem_bytes(nb[i], kTmaConfigs[c->tma_cfg].fs, kTmaConfigs[c->tma_cfg].stages);
+      CU(cudaFuncSetAttribute(f.fn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f.fn[i], TMA_THREADS, smem));
+      c->tma_grid[c->tma_cfg][i] = std::max(1, per_sm) * prop.multiProcessorCount;
     }
   }
   if (c->bev_grid[0] == 0) {   // persistent grid = resident CTAs of each variant
@@ -691,6 +743,7 @@ int bevk_bev_finalize(bevk_ctx* c) {
     }
   }
   c->planned = true;
+  c->shard.geometry = false;   // slabs follow the masks
   return BEVK_OK;
 }
 
@@ -808,19 +861,25 @@ static int stack_table(bevk_ctx* c, const uint8_t* base, long long stride, int n
   return BEVK_OK;
 }
 
-template <bool BAL>
-static int launch_bev_tma(bevk_ctx* c, const TmaParams& P, int nbu) {
+static int launch_bev_tma(bevk_ctx* c, const TmaParams& P, int nbu, bool bal) {
   const long long units = c->n_tiles * ((P.batch + nbu - 1) / nbu);
-  const int variant = (BAL ? 2 : 0) + (nbu == 4 ? 1 : 0);
-  const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(units, c->tma_grid[variant]));
-  const size_t smem = bev_tma_smem_bytes(nbu, BEVK_TMA_FS, BEVK_TMA_STAGES);
-  if (nbu == 4) k_bev_tma<BAL, 4, BEVK_TMA_FS, BEVK_TMA_STAGES><<<blocks, TMA_THREADS, smem, c->stream>>>(P);
-  else k_bev_tma<BAL, 1, BEVK_TMA_FS, BEVK_TMA_STAGES><<<blocks, TMA_THREADS, smem, c->stream>>>(P);
+  const int variant = (bal ? 2 : 0) + (nbu == 4 ? 1 : 0);
+  const TmaConfig cfg = kTmaConfigs[c->tma_cfg];
+  const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(units, c->tma_grid[c->tma_cfg][variant]));
+  const size_t smem = bev_tma_smem_bytes(nbu, cfg.fs, cfg.stages);
+  void* args[] = {const_cast<TmaParams*>(&P)};
+  CU(cudaLaunchKernel(tma_fns(c->tma_cfg).fn[variant], dim3(blocks), dim3(TMA_THREADS), args, smem, c->stream));
   LAUNCHED(c);
   return BEVK_OK;
 }
 
-static int run_device(bevk_ctx* c, FrameSrc src, int batch, const void* d_car, int flags, void* d_out, int cam_lo, int cam_hi) {
+// Output window of a render: the full canvas by default; camera-sharded runs render the tile-aligned bounding box of
+// their cameras' masks ("slab") with its own pitch and frame-set stride.
+struct OutWin { int pitch = 0, ox = 0, oy = 0, ox1 = 0, oy1 = 0; long long stride = 0; };
+
+static int run_device(bevk_ctx* c, FrameSrc src, int batch, const void* d_car, int flags, void* d_out, int cam_lo, int cam_hi,
+                      const OutWin* win = nullptr) {
+  NvtxRange nvtx_render("bevk render (fused BEV kernels)");
   if (!c->planned) return fail(BEVK_ERR_ARG, "bevk_bev_finalize not called");
   if ((!src.table && !src.base) || !d_out) return fail(BEVK_ERR_ARG, "null device pointer");
   if (batch < 1 || batch > 65535) return fail(BEVK_ERR_ARG, "batch %d out of range [1,65535]", batch);
@@ -832,6 +891,11 @@ static int run_device(bevk_ctx* c, FrameSrc src, int batch, const void* d_car, i
   P.tiles = c->d_tiles.as<int4>(); P.items = c->d_items.as<BevItem>(); P.lut = c->d_lut.as<uint4>();
   P.out = reinterpret_cast<uint8_t*>(d_out); P.BW = c->BW; P.BH = c->BH;
   P.canvas_bytes = (long long)c->BW * c->BH * 3;
+  P.out_pitch = c->BW * 3; P.ox = 0; P.oy = 0; P.ox1 = c->BW; P.oy1 = c->BH;
+  if (win) {
+    if (bal || d_car) return fail(BEVK_ERR_ARG, "balance and the car overlay need the full canvas");
+    P.canvas_bytes = win->stride; P.out_pitch = win->pitch; P.ox = win->ox; P.oy = win->oy; P.ox1 = win->ox1; P.oy1 = win->oy1;
+  }
   P.car = reinterpret_cast<const uint8_t*>(d_car);
   P.cam_lo = cam_lo; P.cam_hi = cam_hi;
   P.n_tiles = (int)c->n_tiles; P.batch = batch;
@@ -883,7 +947,8 @@ static int run_device(bevk_ctx* c, FrameSrc src, int batch, const void* d_car, i
     T.tiles = c->d_ttiles.as<int4>(); T.items = c->d_titems.as<TmaItem>(); T.lut = c->d_tlut.as<uint4>();
     T.n_tiles = P.n_tiles; T.batch = batch; T.out = P.out; T.BW = P.BW; T.BH = P.BH; T.canvas_bytes = P.canvas_bytes;
     T.car = P.car; T.csum = P.csum; T.cam_lo = cam_lo; T.cam_hi = cam_hi;
-    if (bal) RET(launch_bev_tma<true>(c, T, nbu)); else RET(launch_bev_tma<false>(c, T, nbu));
+    T.out_pitch = P.out_pitch; T.ox = P.ox; T.oy = P.oy; T.ox1 = P.ox1; T.oy1 = P.oy1;
+    RET(launch_bev_tma(c, T, nbu, bal));
     c->last_path = 2;
   } else {
     if (!gsrc.table) RET(stack_table(c, gsrc.base, gsrc.stride, nf, &gsrc.table));
@@ -1012,6 +1077,7 @@ int bevk_sat_sum_device(bevk_ctx* c, const void* const* parts, int n, uint64_t b
 
 int bevk_bev_run(bevk_ctx* c, const uint8_t* const* srcs, int64_t src_stride, int batch, const uint8_t* car, int flags,
                  uint8_t* out) {
+  NvtxRange nvtx_call("bevk_bev_run (host frames -> host canvases)");
   RET(use(c));
   if (!c->planned) return fail(BEVK_ERR_ARG, "bevk_bev_finalize not called");
   if (!srcs || !out) return fail(BEVK_ERR_ARG, "null host pointer");
@@ -1076,6 +1142,7 @@ int bevk_bev_run(bevk_ctx* c, const uint8_t* const* srcs, int64_t src_stride, in
   for (int b0 = 0; b0 < batch; b0 += chunk, half ^= 1) {
     const int nb = std::min(chunk, batch - b0);
     uint8_t* dframes = c->d_frames.as<uint8_t>() + (size_t)half * chunk * set_frames * fpad;
+    std::unique_ptr<NvtxRange> nvtx_ingest(new NvtxRange("bevk ingest (H2D / zero-copy spans)"));
     CU(cudaStreamWaitEvent(c->copy_stream, c->ev_free[half], 0));   // this half's previous chunk has been rendered
     if (zero_copy) {
       const uint8_t** hp = c->h_hptrs + (size_t)half * chunk * set_frames;
@@ -1112,6 +1179,7 @@ int bevk_bev_run(bevk_ctx* c, const uint8_t* const* srcs, int64_t src_stride, in
       }
     }
     CU(cudaEventRecord(c->ev_in[half], c->copy_stream));
+    nvtx_ingest.reset();
     CU(cudaStreamWaitEvent(c->stream, c->ev_in[half], 0));
     c->timed = false;
     uint8_t* dcanvas = c->d_canvas.as<uint8_t>() + (size_t)half * chunk * cbytes;
@@ -1120,7 +1188,10 @@ int bevk_bev_run(bevk_ctx* c, const uint8_t* const* srcs, int64_t src_stride, in
     fsrc.table = dptrs;
     RET(run_device(c, fsrc, nb, car ? c->d_car.p : nullptr, flags, dcanvas, 0, BEVK_MAX_CAMERAS));
     CU(cudaEventRecord(c->ev_free[half], c->stream));               // frames of this half are free again
-    CU(cudaMemcpyAsync(out + (size_t)b0 * cbytes, dcanvas, cbytes * nb, cudaMemcpyDeviceToHost, c->stream));
+    {
+      NvtxRange nvtx_d2h("bevk read-back (D2H canvases)");
+      CU(cudaMemcpyAsync(out + (size_t)b0 * cbytes, dcanvas, cbytes * nb, cudaMemcpyDeviceToHost, c->stream));
+    }
   }
   CU(cudaStreamSynchronize(c->stream));
   return BEVK_OK;
@@ -1215,6 +1286,186 @@ int bevk_luminance_balance(bevk_ctx* c, const uint8_t* const* imgs, int n, int w
   CU(cudaStreamSynchronize(c->stream));   // also keeps the stack-resident ptrs[] alive long enough
   return BEVK_OK;
 }
+
+// ------------------------------------------------------------------ multi-GPU sharding (one process per GPU)
+// NCCL is loaded at run time (dlopen): libbevk.so has no link-time dependency on it, and a process that already holds
+// a libnccl.so.2 (torch's) shares it.
+namespace {
+struct NcclId { char b[128]; };   // ncclUniqueId (passed by value to ncclCommInitRank)
+struct Nccl {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+Nccl& nccl() {
+  static Nccl n;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      n.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (n.lib) break;
+    }
+    if (n.lib) {
+      n.GetUniqueId = reinterpret_cast<decltype(n.GetUniqueId)>(dlsym(n.lib, "ncclGetUniqueId"));
+      n.CommInitRank = reinterpret_cast<decltype(n.CommInitRank)>(dlsym(n.lib, "ncclCommInitRank"));
+      n.CommDestroy = reinterpret_cast<decltype(n.CommDestroy)>(dlsym(n.lib, "ncclCommDestroy"));
+      n.AllGather = reinterpret_cast<decltype(n.AllGather)>(dlsym(n.lib, "ncclAllGather"));
+      n.GetErrorString = reinterpret_cast<decltype(n.GetErrorString)>(dlsym(n.lib, "ncclGetErrorString"));
+      n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllGather && n.GetErrorString;
+    }
+  }
+  return n;
+}
+const int kNcclUint8 = 1;   // ncclUint8 (nccl.h: ncclInt8 = 0, ncclUint8 = 1)
+}  // namespace
+
+static void shard_release(bevk_ctx* c) {
+  if (c->shard.comm && nccl().ok) nccl().CommDestroy(c->shard.comm);
+  c->shard.comm = nullptr;
+  c->shard.d_slabs.release();
+}
+
+int bevk_shard_configure(bevk_ctx* c, int policy, int rank, int world) {
+  RET(use(c));
+  if (policy != BEVK_SHARD_FRAMES && policy != BEVK_SHARD_CAMERAS) return fail(BEVK_ERR_ARG, "bad policy %d", policy);
+  if (world < 1 || rank < 0 || rank >= world) return fail(BEVK_ERR_ARG, "rank %d outside world %d", rank, world);
+  if (policy == BEVK_SHARD_CAMERAS && world > SHARD_MAX_RANKS)
+    return fail(BEVK_ERR_UNSUPPORTED, "camera sharding supports up to %d ranks (there are at most %d cameras)", SHARD_MAX_RANKS, BEVK_MAX_CAMERAS);
+  if (c->shard.comm && (c->shard.rank != rank || c->shard.world != world)) shard_release(c);
+  c->shard.configured = true; c->shard.geometry = false;
+  c->shard.policy = policy; c->shard.rank = rank; c->shard.world = world;
+  return BEVK_OK;
+}
+
+static int shard_geometry(bevk_ctx* c) {
+  bevk_ctx::Shard& s = c->shard;
+  if (!s.configured) return fail(BEVK_ERR_ARG, "bevk_shard_configure not called");
+  if (!c->planned) return fail(BEVK_ERR_ARG, "bevk_bev_finalize not called");
+  if (s.geometry) return BEVK_OK;
+  std::vector<const uint8_t*> pm(c->n_cam);
+  for (int k = 0; k < c->n_cam; ++k) pm[k] = c->cam[k].mask.data();
+  s.slab_bytes = 0;
+  for (int r = 0; r < s.world && r < SHARD_MAX_RANKS; ++r) {
+    shard_block(c->n_cam, r, s.world, &s.cam_lo[r], &s.cam_hi[r]);
+    s.rect[r] = slab_rect(pm.data(), s.cam_lo[r], s.cam_hi[r], c->BW, c->BH);
+    const long long bytes = (long long)(s.rect[r].ox1 - s.rect[r].ox) * (s.rect[r].oy1 - s.rect[r].oy) * 3;
+    s.slab_bytes = std::max(s.slab_bytes, bytes);
+  }
+  s.slab_bytes = (s.slab_bytes + 255) & ~255ll;   // equal counts for the all-gather, 256-byte aligned slabs
+  s.geometry = true;
+  return BEVK_OK;
+}
+
+int bevk_shard_unique_id(void* id, int len) {
+  if (!id || len < 128) return fail(BEVK_ERR_ARG, "id buffer must hold 128 bytes");
+  if (!nccl().ok) return fail(BEVK_ERR_UNSUPPORTED, "NCCL (libnccl.so.2) could not be loaded: %s", dlerror() ? dlerror() : "missing symbols");
+  NcclId u;
+  const int r = nccl().GetUniqueId(&u);
+  if (r != 0) return fail(BEVK_ERR_CUDA, "ncclGetUniqueId: %s", nccl().GetErrorString(r));
+  memcpy(id, &u, 128);
+  return BEVK_OK;
+}
+
+int bevk_shard_connect(bevk_ctx* c, const void* id, int len) {
+  RET(use(c));
+  if (!c->shard.configured) return fail(BEVK_ERR_ARG, "bevk_shard_configure not called");
+  if (!id || len < 128) return fail(BEVK_ERR_ARG, "id must be the 128 bytes bevk_shard_unique_id produced on one rank");
+  if (!nccl().ok) return fail(BEVK_ERR_UNSUPPORTED, "NCCL (libnccl.so.2) could not be loaded");
+  if (c->shard.comm) { nccl().CommDestroy(c->shard.comm); c->shard.comm = nullptr; }
+  NcclId u;
+  memcpy(&u, id, 128);
+  const int r = nccl().CommInitRank(&c->shard.comm, c->shard.world, u, c->shard.rank);
+  if (r != 0) { c->shard.comm = nullptr; return fail(BEVK_ERR_CUDA, "ncclCommInitRank(rank %d of %d): %s", c->shard.rank, c->shard.world, nccl().GetErrorString(r)); }
+  return BEVK_OK;
+}
+
+int bevk_shard_info(bevk_ctx* c, int rank, int* cam_lo, int* cam_hi, int32_t rect[4], int64_t* slab_bytes) {
+  RET(use(c));
+  RET(shard_geometry(c));
+  if (rank < 0 || rank >= c->shard.world || rank >= SHARD_MAX_RANKS) return fail(BEVK_ERR_ARG, "rank %d out of range", rank);
+  if (cam_lo) *cam_lo = c->shard.cam_lo[rank];
+  if (cam_hi) *cam_hi = c->shard.cam_hi[rank];
+  if (rect) { rect[0] = c->shard.rect[rank].ox; rect[1] = c->shard.rect[rank].oy; rect[2] = c->shard.rect[rank].ox1; rect[3] = c->shard.rect[rank].oy1; }
+  if (slab_bytes) *slab_bytes = c->shard.slab_bytes;
+  return BEVK_OK;
+}
+
+// rank `as_rank`'s slabs of `batch` frame-sets into d_slabs[as_rank][batch][slab_bytes]
+static int shard_render(bevk_ctx* c, FrameSrc src, int batch, int as_rank, void* d_slabs) {
+  bevk_ctx::Shard& s = c->shard;
+  const SlabRect q = s.rect[as_rank];
+  uint8_t* dst = reinterpret_cast<uint8_t*>(d_slabs) + (size_t)as_rank * batch * s.slab_bytes;
+  if (q.ox1 <= q.ox || s.cam_hi[as_rank] <= s.cam_lo[as_rank]) return BEVK_OK;   // a rank without cameras contributes nothing
+  OutWin w;
+  w.pitch = (q.ox1 - q.ox) * 3; w.ox = q.ox; w.oy = q.oy; w.ox1 = q.ox1; w.oy1 = q.oy1; w.stride = s.slab_bytes;
+  return run_device(c, src, batch, nullptr, 0, dst, s.cam_lo[as_rank], s.cam_hi[as_rank], &w);
+}
+
+static int shard_compose(bevk_ctx* c, const void* d_slabs, int batch, const void* d_car, void* d_out) {
+  bevk_ctx::Shard& s = c->shard;
+  ComposeArgs a{};
+  a.slabs = reinterpret_cast<const uint8_t*>(d_slabs); a.slab_bytes = s.slab_bytes; a.world = std::min(s.world, SHARD_MAX_RANKS);
+  a.batch = batch; a.BW = c->BW; a.BH = c->BH;
+  for (int r = 0; r < a.world; ++r) a.rect[r] = s.rect[r];
+  a.car = reinterpret_cast<const uint8_t*>(d_car); a.out = reinterpret_cast<uint8_t*>(d_out);
+  const long long total = (long long)c->BW * c->BH * 3;
+  const bool word = (c->BW % 4) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 3) == 0 && (!d_car || (reinterpret_cast<uintptr_t>(d_car) & 3) == 0) &&
+                    (reinterpret_cast<uintptr_t>(d_slabs) & 3) == 0;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(148 * 8 / std::max(1, std::min(batch, 64)) + 1, total / (4 * 256) + 1));
+  if (word) k_compose_slabs<true><<<dim3(blocks, batch), 256, 0, c->stream>>>(a);
+  else k_compose_slabs<false><<<dim3(blocks, batch), 256, 0, c->stream>>>(a);
+  LAUNCHED(c);
+  return BEVK_OK;
+}
+
+int bevk_shard_render(bevk_ctx* c, const void* d_frames, int64_t frame_stride, int batch, int as_rank, void* d_slabs) {
+  RET(use(c));
+  RET(shard_geometry(c));
+  RET(check_stack(c, d_frames, frame_stride));
+  if (as_rank < 0 || as_rank >= c->shard.world || as_rank >= SHARD_MAX_RANKS) return fail(BEVK_ERR_ARG, "rank %d out of range", as_rank);
+  if (!d_slabs || (reinterpret_cast<uintptr_t>(d_slabs) & 15)) return fail(BEVK_ERR_ARG, "slab buffer null or not 16-byte aligned");
+  c->timed = true;
+  return shard_render(c, stack_src(d_frames, frame_stride), batch, as_rank, d_slabs);
+}
+
+int bevk_shard_compose(bevk_ctx* c, const void* d_slabs, int batch, const void* d_car, void* d_out) {
+  RET(use(c));
+  RET(shard_geometry(c));
+  if (!d_slabs || !d_out || batch < 1) return fail(BEVK_ERR_ARG, "bad argument");
+  return shard_compose(c, d_slabs, batch, d_car, d_out);
+}
+
+int bevk_bev_run_sharded(bevk_ctx* c, const void* d_frames, int64_t frame_stride, int batch, const void* d_car, int flags, void* d_out) {
+  NvtxRange nvtx_call("bevk_bev_run_sharded (render slabs, all-gather, compose)");
+  RET(use(c));
+  if (!c->shard.configured) return fail(BEVK_ERR_ARG, "bevk_shard_configure not called");
+  RET(check_stack(c, d_frames, frame_stride));
+  bevk_ctx::Shard& s = c->shard;
+  s.last_link_bytes = 0;
+  if (s.policy == BEVK_SHARD_FRAMES || s.world == 1) {   // every rank renders its own frame-sets: no exchange
+    c->timed = true;
+    return run_device(c, stack_src(d_frames, frame_stride), batch, d_car, flags, d_out, 0, BEVK_MAX_CAMERAS);
+  }
+  if (flags & BEVK_FLAG_BALANCE) return fail(BEVK_ERR_UNSUPPORTED, "balance needs every camera's V mean before the warp: not available with camera sharding");
+  if (!s.comm) return fail(BEVK_ERR_ARG, "bevk_shard_connect not called");
+  RET(shard_geometry(c));
+  const size_t per_rank = (size_t)batch * s.slab_bytes;
+  RET(s.d_slabs.ensure(per_rank * s.world));
+  c->timed = false;
+  RET(shard_render(c, stack_src(d_frames, frame_stride), batch, s.rank, s.d_slabs.p));
+  // ONE all-gather of the slabs (in place: this rank's block is already where it belongs)
+  const int r = nccl().AllGather(s.d_slabs.as<uint8_t>() + per_rank * s.rank, s.d_slabs.p, per_rank, kNcclUint8, s.comm, c->stream);
+  if (r != 0) return fail(BEVK_ERR_CUDA, "ncclAllGather: %s", nccl().GetErrorString(r));
+  s.last_link_bytes = (long long)per_rank * (s.world - 1);
+  return shard_compose(c, s.d_slabs.p, batch, d_car, d_out);
+}
+
+int64_t bevk_shard_last_link_bytes(bevk_ctx* c) { return c ? c->shard.last_link_bytes : 0; }
 
 // ------------------------------------------------------------------ CUDA graphs
 // Stream capture of whatever the device-pointer entry points enqueue between begin and end; replayed with one call.

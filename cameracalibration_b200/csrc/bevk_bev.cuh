@@ -54,6 +54,8 @@ struct BevParams {
   const uint8_t* car;
   unsigned long long* csum;     // [batch * 3] channel sums of the composed canvas (BALANCE)
   int cam_lo, cam_hi;
+  // output window (see TmaParams): canvas pixels [ox,ox1) x [oy,oy1) -> out + (y-oy)*out_pitch + (x-ox)*3
+  int out_pitch, ox, oy, ox1, oy1;
 };
 
 // read-only global loads; the host forms serve tests/host/kernel_math.cu
@@ -224,17 +226,18 @@ __global__ void __launch_bounds__(256, BEVK_MIN_CTAS) k_bev(BevParams P) {
       first = false;
       __syncthreads();
     }
+    if (tile.x >= P.ox1 || tile.x + TILE <= P.ox || tile.y >= P.oy1 || tile.y + TILE <= P.oy) continue;   // outside the output window
 #if BEVK_WRITE_COALESCED
     // Experiment (default off, not yet measured): interior tiles are written as 3 x 256 consecutive 32-bit
     // words of the tile's 32 rows x 24 words, so one warp store covers 2 canvas rows (about 3 L1 tag look-ups)
     // instead of 8 lanes x 4 rows at a 12-byte stride (6.5 look-ups, profiles/r01_k_bev_source_summary.txt).
-    if (!BAL && tile.x + TILE <= P.BW && (P.BW * 3) % 4 == 0 && P.canvas_bytes % 4 == 0) {
+    if (!BAL && tile.x + TILE <= P.ox1 && P.out_pitch % 4 == 0 && P.canvas_bytes % 4 == 0 && P.ox % 4 == 0) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         const int idx = i * 256 + t, r = idx / 24, w = idx - r * 24;     // word w of tile row r
         const int gy = tile.y + r;
-        if (gy >= P.BH) continue;
-        const size_t word_off = ((size_t)gy * P.BW * 3 + (size_t)tile.x * 3) / 4 + w;
+        if (gy >= P.oy1) continue;
+        const size_t word_off = ((size_t)(gy - P.oy) * P.out_pitch + (size_t)(tile.x - P.ox) * 3) / 4 + w;
         const unsigned cw = P.car ? __ldg(reinterpret_cast<const unsigned*>(P.car) + word_off) : 0u;
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
@@ -250,10 +253,10 @@ __global__ void __launch_bounds__(256, BEVK_MIN_CTAS) k_bev(BevParams P) {
     // ---- write the tile(s): thread t -> row t/8, 4 pixels (12 bytes) at pixel 4*(t%8) ----
     const int row = t >> 3, chunk = t & 7;
     const int gy = tile.y + row, gx = tile.x + chunk * 4;
-    const bool inb = (gy < P.BH) && (gx < P.BW);
-    const size_t pix_off = (size_t)gy * P.BW * 3 + (size_t)gx * 3;
-    const bool full = inb && (gx + 4 <= P.BW) && ((P.BW * 3) % 4 == 0) && (P.canvas_bytes % 4 == 0);
-    const int npx = inb ? min(4, P.BW - gx) : 0;
+    const bool inb = (gy < P.oy1) && (gx < P.ox1);
+    const size_t pix_off = (size_t)(gy - P.oy) * P.out_pitch + (size_t)(gx - P.ox) * 3;
+    const bool full = inb && (gx + 4 <= P.ox1) && (P.out_pitch % 4 == 0) && (P.canvas_bytes % 4 == 0) && (P.ox % 4 == 0);
+    const int npx = inb ? min(4, P.ox1 - gx) : 0;
     unsigned c0 = 0, c1 = 0, c2 = 0;
     if (!BAL && P.car && full) {
       const unsigned* c = reinterpret_cast<const unsigned*>(P.car + pix_off);

@@ -13,8 +13,11 @@
 //   * the eight consumer warps read their taps from shared memory (LDS with immediate offsets for frame-set and
 //     word; ~1.6 bank wavefronts per load instead of 4.4 L1 tag look-ups per global load, profiles/), and release
 //     the stage through a second mbarrier;
-//   * strips whose box would not fit a stage (heavily minified near field, discontinuities of the LUT) are GATHER
-//     items: their entries carry global byte offsets and take the 32-bit global loads of the round-1 kernel.
+//   * a stage holds 4 FS bytes: the boxes of four frame-sets of FS bytes each, or -- for the heavily minified near
+//     field, where 256 samples need 12-24 KB of source -- two boxes of 2 FS or one of 4 FS; such items take 2 or 4
+//     PASSES over their entries, one ring slot per pass.  Only what does not even fit 4 FS (discontinuities of the
+//     LUT, about 1 % of the entries) is a GATHER item: entries carry global byte offsets and take the 32-bit
+//     global loads of the round-1 kernel.
 //
 // LUT entry (16 B, thread order t = warp*32 + lane, group k: canvas line k*8 + warp, position lane along it):
 //   .x  TMA item: byte offset of the aligned word holding tap (sy,sx) inside the frame-set's staged box | the same
@@ -39,7 +42,8 @@ struct __align__(16) TmaItem {   // 32 B, read as two 16-byte words
   int xw;                        // box origin: word column (may be negative) ...
   int y;                         // ... and row; TMA zero-fills what lies outside the frame
   unsigned tx_bytes;             // bytes the box of ONE frame-set delivers
-  int pad0, pad1;
+  int fs_bytes;                  // stage bytes reserved per frame-set: FS, 2 FS or 4 FS (a stage holds 4, 2 or 1 frame-sets)
+  int pad1;
 };
 static_assert(sizeof(TmaItem) == 32, "TmaItem is read as two int4");
 
@@ -53,10 +57,13 @@ struct TmaParams {
   const TmaItem* items;
   const uint4* lut;
   int n_tiles, batch;
-  uint8_t* out; int BW, BH; long long canvas_bytes;
+  uint8_t* out; int BW, BH; long long canvas_bytes;   // canvas_bytes: stride between the frame-sets' outputs
   const uint8_t* car;
   unsigned long long* csum;
   int cam_lo, cam_hi;
+  // output window (camera-sharded runs render only the tile-aligned bounding box of their cameras' masks, a "slab"):
+  // canvas pixels [ox,ox1) x [oy,oy1) go to out + (y-oy)*out_pitch + (x-ox)*3; the full canvas is 0,0,BW,BH, pitch 3*BW
+  int out_pitch, ox, oy, ox1, oy1;
 };
 
 // The six words of one entry -> three sums whose byte 2 is the interpolated channel.
@@ -118,6 +125,17 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       "bra W_%=;\n\t"
       "D_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
+// producer-side wait: one thread per CTA polls; back off between polls so that it does not take issue slots from the
+// eight consumer warps of its own and the neighbouring CTAs (profiles/r02_b: 3.4 M polls per launch without it)
+__device__ __forceinline__ void mbar_wait_backoff(unsigned bar, unsigned parity) {
+  unsigned done = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(200);
+  }
+}
 __device__ __forceinline__ void tma_load_3d(unsigned dst, const void* map, int x, int y, int z, unsigned bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
@@ -137,19 +155,15 @@ __device__ __forceinline__ unsigned lds32_if(unsigned addr, unsigned pred) {
 __device__ __forceinline__ void sts32(unsigned addr, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory"); }
 
-#ifndef BEVK_TMA_MIN_CTAS
-#define BEVK_TMA_MIN_CTAS 3
-#endif
-
 constexpr size_t bev_tma_smem_bytes(int nb, int fs, int stages) {
-  return (size_t)stages * nb * fs + (size_t)nb * ACC_WORDS * 4 + (size_t)stages * 16 + 1024;   // + alignment slack
+  return (size_t)stages * 4 * fs + (size_t)nb * ACC_WORDS * 4 + (size_t)stages * 16 + 1024;   // + alignment slack
 }
 
 // GATHER items (boxes that do not fit a stage): one entry applied to the NB frame-sets of the unit, taps from global
 // memory as in the round-1 kernel.  `aa`: shared address of the entry's accumulator word of frame-set 0.
 template <int NB>
 __device__ __forceinline__ void gather_entry(const TmaParams& P, const uint4 e, unsigned aa, bool first, bool nosat,
-                                             const uint8_t* frame0, long long set_stride) {
+                                             const uint8_t* frame0, long long set_stride, int nb) {
   if (!(e.w & T_ACTIVE)) {
     if (first) {
 #pragma unroll
@@ -162,7 +176,7 @@ __device__ __forceinline__ void gather_entry(const TmaParams& P, const uint4 e, 
     const unsigned ew = (e.w & 0x1ffffu) | (((e.w >> 19) & 1023u) << 17);   // sample_slow's layout: weight | fraction << 17
 #pragma unroll 1
     for (int j = 0; j < NB; ++j) {
-      unsigned v = sample_slow(geo, frame0 + j * set_stride, e.x, ew);
+      unsigned v = sample_slow(geo, frame0 + (j < nb ? j : 0) * set_stride, e.x, ew);   // the batch tail aliases frame-set 0: never written out
       if (!first) v = sat_add_bgr(v, lds32(aa + j * ACC_WORDS * 4));
       sts32(aa + j * ACC_WORDS * 4, v);
     }
@@ -172,7 +186,7 @@ __device__ __forceinline__ void gather_entry(const TmaParams& P, const uint4 e, 
   const bool third = sh8 == 24u;
 #pragma unroll 2
   for (int j = 0; j < NB; ++j) {
-    const uint8_t* q0 = frame0 + j * set_stride + off_al;
+    const uint8_t* q0 = frame0 + (j < nb ? j : 0) * set_stride + off_al;
     const uint8_t* q1 = q0 + P.pitch;
     const unsigned a0 = ldg32(q0), a1 = ldg32(q0 + 4), a2 = third ? ldg32(q0 + 8) : 0u;
     const unsigned b0 = ldg32(q1), b1 = ldg32(q1 + 4), b2 = third ? ldg32(q1 + 8) : 0u;
@@ -187,9 +201,10 @@ __device__ __forceinline__ void gather_entry(const TmaParams& P, const uint4 e, 
   }
 }
 
-// TMA items: the groups [k0,k1) of one LUT block applied to the NB staged boxes.  FIRST: this camera stores (zeros where
-// its mask is 0), later cameras add; FULL: every weight of the item is 255.
-template <int NB, int FS, bool FIRST, bool FULL>
+// TMA items: the groups [k0,k1) of one LUT block applied to NBP staged boxes (one pass).  RS: stage bytes between the
+// boxes of consecutive frame-sets.  FIRST: this camera stores (zeros where its mask is 0), later cameras add; FULL: every
+// weight of the item is 255.
+template <int NBP, int RS, bool FIRST, bool FULL>
 __device__ __forceinline__ void tma_item(const uint4* __restrict__ L, int k0, int k1, unsigned sbase, unsigned aa, unsigned astep,
                                          bool nosat) {
   L += k0 * 256;
@@ -203,39 +218,56 @@ __device__ __forceinline__ void tma_item(const uint4* __restrict__ L, int k0, in
     if (!(e.w & T_ACTIVE)) {
       if (FIRST) {
 #pragma unroll
-        for (int j = 0; j < NB; ++j) sts32(aa + j * ACC_WORDS * 4, 0u);
+        for (int j = 0; j < NBP; ++j) sts32(aa + j * ACC_WORDS * 4, 0u);
       }
       continue;
     }
     const unsigned o0 = sbase + (e.x & 0xffffu), o1 = sbase + (e.x >> 16);
     const unsigned sh8 = (e.w >> 14) & 24u, wm = e.w & 0x1ffffu, third = sh8 == 24u;
-    unsigned a0[NB], a1[NB], a2[NB], b0[NB], b1[NB], b2[NB];
+    // two frame-sets at a time: 12 words in flight cover the shared-memory latency, and the register budget allows three
+    // CTAs per SM (24 words in flight cost an occupancy step for nothing)
+    constexpr int G = NBP < 2 ? 1 : 2;
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      a0[j] = lds32(o0 + j * FS); a1[j] = lds32(o0 + j * FS + 4); a2[j] = lds32_if(o0 + j * FS + 8, third);
-      b0[j] = lds32(o1 + j * FS); b1[j] = lds32(o1 + j * FS + 4); b2[j] = lds32_if(o1 + j * FS + 8, third);
-    }
+    for (int h = 0; h < NBP; h += G) {
+      unsigned a0[G], a1[G], a2[G], b0[G], b1[G], b2[G];
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      unsigned sb, sg, sr;
-      interp_sums(sh8, e.y, e.z, a0[j], a1[j], a2[j], b0[j], b1[j], b2[j], sb, sg, sr);
-      unsigned v = weight_pack<FULL>(sb, sg, sr, wm);
-      if (!FIRST) {
-        const unsigned old = lds32(aa + j * ACC_WORDS * 4);
-        v = nosat ? v + old : sat_add_bgr(v, old);                        // cv2.add chain, reference camera order
+      for (int j = 0; j < G; ++j) {
+        const unsigned r0 = o0 + (h + j) * RS, r1 = o1 + (h + j) * RS;
+        a0[j] = lds32(r0); a1[j] = lds32(r0 + 4); a2[j] = lds32_if(r0 + 8, third);
+        b0[j] = lds32(r1); b1[j] = lds32(r1 + 4); b2[j] = lds32_if(r1 + 8, third);
       }
-      sts32(aa + j * ACC_WORDS * 4, v);
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        unsigned sb, sg, sr;
+        interp_sums(sh8, e.y, e.z, a0[j], a1[j], a2[j], b0[j], b1[j], b2[j], sb, sg, sr);
+        unsigned v = weight_pack<FULL>(sb, sg, sr, wm);
+        if (!FIRST) {
+          const unsigned old = lds32(aa + (h + j) * ACC_WORDS * 4);
+          v = nosat ? v + old : sat_add_bgr(v, old);                      // cv2.add chain, reference camera order
+        }
+        sts32(aa + (h + j) * ACC_WORDS * 4, v);
+      }
     }
   }
 }
 
-template <bool BAL, int NB, int FS, int STAGES>
-__global__ void __launch_bounds__(TMA_THREADS, BEVK_TMA_MIN_CTAS) k_bev_tma(const TmaParams P) {
+// one pass of a TMA item: NBP frame-sets whose boxes lie RS bytes apart in the stage
+template <int NBP, int RS>
+__device__ __forceinline__ void tma_pass(const uint4* __restrict__ L, int k0, int k1, unsigned sbase, unsigned aa, unsigned astep,
+                                         bool first, bool full, bool nosat) {
+  if (!first) tma_item<NBP, RS, false, false>(L, k0, k1, sbase, aa, astep, nosat);
+  else if (NBP == 4 && full) tma_item<NBP, RS, true, true>(L, k0, k1, sbase, aa, astep, nosat);
+  else tma_item<NBP, RS, true, false>(L, k0, k1, sbase, aa, astep, nosat);
+}
+
+template <bool BAL, int NB, int FS, int STAGES, int MINCTAS>
+__global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParams P) {
+  constexpr int SB = 4 * FS;   // bytes of one ring slot
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // stages need 128-byte alignment for cp.async.bulk.tensor; align the base to 1024 (pointer arithmetic only, so the
   // compiler keeps the shared address space)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned* acc = reinterpret_cast<unsigned*>(smem + (size_t)STAGES * NB * FS);   // [NB][ACC_WORDS] packed BGRX
+  unsigned* acc = reinterpret_cast<unsigned*>(smem + (size_t)STAGES * SB);   // [NB][ACC_WORDS] packed BGRX
   const unsigned bar_full = smem_u32(acc + NB * ACC_WORDS), bar_empty = bar_full + 8 * STAGES;
   const unsigned stage0 = smem_u32(smem), acc_u32 = smem_u32(acc);
   __shared__ unsigned long long s_sum[BAL ? 3 * NB : 1];
@@ -253,7 +285,7 @@ __global__ void __launch_bounds__(TMA_THREADS, BEVK_TMA_MIN_CTAS) k_bev_tma(cons
   const long long n_units = (long long)P.n_tiles * groups;
 
   if (t >= TMA_CONSUMERS) {
-    // ---------------- producer: one thread walks the same (unit, item) sequence and keeps the ring full
+    // ---------------- producer: one thread walks the same (unit, item, pass) sequence and keeps the ring full
     if (t == TMA_CONSUMERS) {
       unsigned n = 0;
       for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -266,14 +298,17 @@ __global__ void __launch_bounds__(TMA_THREADS, BEVK_TMA_MIN_CTAS) k_bev_tma(cons
           const int4 i1 = __ldg(reinterpret_cast<const int4*>(P.items + it) + 1);
           const int cam = (short)(i0.y & 0xffff), flags = (i0.y >> 24) & 0xff;
           if (cam < P.cam_lo || cam >= P.cam_hi || (flags & ITEM_GATHER)) continue;
-          const unsigned shape = (unsigned)i0.z >> 16;
-          const unsigned s = n % STAGES, ph = (n / STAGES) & 1u;
-          mbar_wait(bar_empty + 8 * s, ph ^ 1u);           // consumers have left this stage
-          mbar_expect_tx(bar_full + 8 * s, (unsigned)nb * (unsigned)i1.y);
-          const uint8_t* map = P.maps + (size_t)shape * TMA_DESC_BYTES;
-          for (int j = 0; j < nb; ++j)
-            tma_load_3d(stage0 + (s * NB + j) * FS, map, i0.w, i1.x, (b0 + j) * P.n_cam + cam, bar_full + 8 * s);
-          ++n;
+          const uint8_t* map = P.maps + (size_t)((unsigned)i0.z >> 16) * TMA_DESC_BYTES;
+          const int rs = i1.z, fpp = min(NB, SB / rs);     // frame-sets per pass
+          for (int p = 0; p < nb; p += fpp) {
+            const unsigned s = n % STAGES, ph = (n / STAGES) & 1u;
+            const int np = min(fpp, nb - p);
+            mbar_wait_backoff(bar_empty + 8 * s, ph ^ 1u); // consumers have left this slot
+            mbar_expect_tx(bar_full + 8 * s, (unsigned)np * (unsigned)i1.y);
+            for (int j = 0; j < np; ++j)
+              tma_load_3d(stage0 + s * SB + j * rs, map, i0.w, i1.x, (b0 + p + j) * P.n_cam + cam, bar_full + 8 * s);
+            ++n;
+          }
         }
       }
     }
@@ -305,39 +340,46 @@ __global__ void __launch_bounds__(TMA_THREADS, BEVK_TMA_MIN_CTAS) k_bev_tma(cons
       // shared address of this thread's accumulator word of group 0 / step to the next group, frame-set 0
       const unsigned aa = acc_u32 + 4u * (unsigned)(orient ? posy : posx), astep = 4u * (unsigned)(orient ? stepy : stepx);
       if (flags & ITEM_GATHER) {
-        // frame-set j of this unit and camera: frame0 + j * set_stride (the batch tail aliases frame-set b0: computed, never written)
+        // frame-set j of this unit and camera: frame0 + j * set_stride
         const uint8_t* frame0 = P.base + (long long)(b0 * P.n_cam + cam) * P.frame_stride;
-        const long long set_stride = nb == NB ? (long long)P.n_cam * P.frame_stride : 0ll;
+        const long long set_stride = (long long)P.n_cam * P.frame_stride;
         uint4 nxt = __ldg(L + k0 * 256);
 #pragma unroll 1
         for (int k = k0; k < k1; ++k) {
           const uint4 e = nxt;
           if (k + 1 < k1) nxt = __ldg(L + (k + 1) * 256);
-          gather_entry<NB>(P, e, aa + k * astep, first, nosat, frame0, set_stride);
+          gather_entry<NB>(P, e, aa + k * astep, first, nosat, frame0, set_stride, nb);
         }
       } else {
-        const unsigned s = n % STAGES, ph = (n / STAGES) & 1u;
-        const unsigned sbase = stage0 + s * NB * FS;
-        mbar_wait(bar_full + 8 * s, ph);                 // the boxes of all nb frame-sets have landed
-        if (!first) tma_item<NB, FS, false, false>(L, k0, k1, sbase, aa, astep, nosat);
-        else if (flags & ITEM_FULL) tma_item<NB, FS, true, true>(L, k0, k1, sbase, aa, astep, nosat);
-        else tma_item<NB, FS, true, false>(L, k0, k1, sbase, aa, astep, nosat);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_empty + 8 * s);   // this warp no longer reads the stage
-        ++n;
+        const int rs = __ldg(reinterpret_cast<const int*>(P.items + it) + 6);   // TmaItem::fs_bytes
+        const int fpp = min(NB, SB / rs);
+        const bool full = (flags & ITEM_FULL) != 0;
+        for (int p = 0; p < nb; p += fpp) {
+          const unsigned s = n % STAGES, ph = (n / STAGES) & 1u;
+          const unsigned sbase = stage0 + s * SB;
+          mbar_wait(bar_full + 8 * s, ph);               // the boxes of this pass have landed
+          const unsigned ap = aa + (unsigned)p * (ACC_WORDS * 4);
+          if (NB == 4 && fpp == 4) tma_pass<(NB == 4 ? 4 : 1), FS>(L, k0, k1, sbase, ap, astep, first, full, nosat);
+          else if (NB == 4 && fpp == 2) tma_pass<(NB == 4 ? 2 : 1), 2 * FS>(L, k0, k1, sbase, ap, astep, first, full, nosat);
+          else tma_pass<1, 0>(L, k0, k1, sbase, ap, astep, first, full, nosat);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_empty + 8 * s); // this warp no longer reads the slot
+          ++n;
+        }
       }
     }
     const bool none = first_cam < 0;                      // tile without a camera (car hole): zeros
     consumer_sync();
     // ---- write the tile(s)
-    if (!BAL && tile.x + TILE <= P.BW && (P.BW & 3) == 0 && (P.canvas_bytes & 3) == 0) {
+    if (tile.x >= P.ox1 || tile.x + TILE <= P.ox || tile.y >= P.oy1 || tile.y + TILE <= P.oy) continue;   // outside the output window
+    if (!BAL && tile.x + TILE <= P.ox1 && (P.out_pitch & 3) == 0 && (P.canvas_bytes & 3) == 0 && (P.ox & 3) == 0) {
       // interior tile: 32 rows x 24 words, written as 3 x 256 consecutive words (a warp store = two 96-byte row pieces)
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         const int idx = i * 256 + t, r = idx / 24, w = idx - r * 24;
         const int gy = tile.y + r;
-        if (gy >= P.BH) continue;
-        const size_t word_off = ((size_t)gy * P.BW * 3 + (size_t)tile.x * 3) / 4 + w;
+        if (gy >= P.oy1) continue;
+        const size_t word_off = ((size_t)(gy - P.oy) * P.out_pitch + (size_t)(tile.x - P.ox) * 3) / 4 + w;
         const unsigned cw = P.car ? __ldg(reinterpret_cast<const unsigned*>(P.car) + word_off) : 0u;
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
@@ -352,10 +394,10 @@ __global__ void __launch_bounds__(TMA_THREADS, BEVK_TMA_MIN_CTAS) k_bev_tma(cons
     // edge tiles and the BALANCE variant: thread t -> row t/8, 4 pixels (12 bytes) at pixel 4*(t%8)
     const int row = t >> 3, chunk = t & 7;
     const int gy = tile.y + row, gx = tile.x + chunk * 4;
-    const bool inb = (gy < P.BH) && (gx < P.BW);
-    const size_t pix_off = (size_t)gy * P.BW * 3 + (size_t)gx * 3;
-    const bool full = inb && (gx + 4 <= P.BW) && ((P.BW * 3) % 4 == 0) && (P.canvas_bytes % 4 == 0);
-    const int npx = inb ? min(4, P.BW - gx) : 0;
+    const bool inb = (gy < P.oy1) && (gx < P.ox1);
+    const size_t pix_off = (size_t)(gy - P.oy) * P.out_pitch + (size_t)(gx - P.ox) * 3;
+    const bool full = inb && (gx + 4 <= P.ox1) && (P.out_pitch % 4 == 0) && (P.canvas_bytes % 4 == 0) && (P.ox % 4 == 0);
+    const int npx = inb ? min(4, P.ox1 - gx) : 0;
     unsigned c0 = 0, c1 = 0, c2 = 0;
     if (!BAL && P.car && full) {
       const unsigned* c = reinterpret_cast<const unsigned*>(P.car + pix_off);

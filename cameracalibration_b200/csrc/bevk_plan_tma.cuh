@@ -5,9 +5,13 @@
 // camera's mask (Mask / BlendMask, :119-280).  Output, per canvas tile of 32x32 px and per camera whose mask touches it:
 //   * one LUT block of 1024 thread-ordered entries (layout in bevk_bev_tma.cuh);
 //   * one or more ITEMS covering the block's four groups of eight canvas lines.  An item whose taps fit a source box
-//     of at most `stage_bytes` is a TMA item (box origin, tensor-map shape index, bytes); the range is halved until
-//     that holds, and an 8-line strip that still does not fit becomes a GATHER item (global loads).
-// Box shapes are quantised to a small menu so that a few dozen tensor maps serve the whole plan.
+//     of at most FS = `stage_bytes` is a TMA item (box origin, tensor-map shape index, bytes) whose four frame-sets
+//     share a ring slot of 4 FS; the range is halved until that holds; an 8-line strip that still does not fit gets
+//     2 FS (two frame-sets per pass) or 4 FS (one per pass), and only what exceeds 4 FS is a GATHER item (global loads).
+//   * the box pitch is chosen among the next few 16-byte multiples to minimise the shared-memory bank conflicts of the
+//     item's own warp loads (simulated here: the lanes of a warp follow a curved path through the box).
+// Box shapes are quantised to a small menu so that a few dozen tensor maps serve the whole plan.  Tiles are ordered by
+// decreasing estimated cost, so that the persistent CTAs' last rounds are the cheap ones.
 #pragma once
 #include <algorithm>
 #include <climits>
@@ -42,6 +46,23 @@ inline int menu_h(int h) {
   return (h + 15) & ~15;
 }
 
+// bank-conflict degree of one warp-wide 32-bit shared load: the largest number of distinct words that share a bank
+inline int lds_wavefronts(const unsigned* word, int n) {
+  unsigned seen[32][4];
+  int cnt[32] = {0};
+  int deg = 0;
+  for (int i = 0; i < n; ++i) {
+    const unsigned b = word[i] & 31u;
+    bool dup = false;
+    for (int j = 0; j < cnt[b] && j < 4; ++j) dup |= seen[b][j] == word[i];
+    if (dup) continue;
+    if (cnt[b] < 4) seen[b][cnt[b]] = word[i];
+    cnt[b]++;
+    if (cnt[b] > deg) deg = cnt[b];
+  }
+  return deg;
+}
+
 inline void build_tma_plan(int NC, int FW, int FH, int BW, int BH, bool nearest, const short* const* m1,
                            const unsigned short* const* m2, const uint8_t* const* masks, int stage_bytes, bool allow_tma,
                            TmaPlan& out) {
@@ -55,10 +76,12 @@ inline void build_tma_plan(int NC, int FW, int FH, int BW, int BH, bool nearest,
   const bool tma_ok = allow_tma && (pitch % 16u) == 0;
   struct Ent { int sx, sy; unsigned frac, w; bool active; };
   std::vector<Ent> ent(TILE * TILE);
+  std::vector<long long> tile_cost;
   for (int tj = 0; tj < ty; ++tj)
     for (int ti = 0; ti < tx; ++ti) {
       const int x0 = ti * TILE, y0 = tj * TILE;
       int4 t = make_int4(x0, y0, (int)out.items.size(), 0);
+      long long item_cost = 64;   // write-out
       // can cv2.add saturate anywhere on this tile?  (blend weights of the reference sum to <= 255: never)
       bool nosat = true;
       for (int y = y0; y < std::min(y0 + TILE, BH) && nosat; ++y)
@@ -126,14 +149,19 @@ inline void build_tma_plan(int NC, int FW, int FH, int BW, int BH, bool nearest,
           it.k0 = (unsigned char)r.g0; it.k1 = (unsigned char)r.g1;
           it.flags = (unsigned char)((nosat ? ITEM_NOSAT : 0) | (full ? ITEM_FULL : 0));
           bool fits = false;
-          int bx0 = 0, w16 = 0, hh = 0;
+          int bx0 = 0, w16 = 0, hh = 0, fs_bytes = stage_bytes;
           if (n_act && tma_ok) {
             bx0 = floor_div(wx0, 4) * 4;                       // 16-byte aligned box origin (in words)
             w16 = menu_w16((wx1 - bx0 + 3) / 4);
             hh = menu_h(ry1 - ry0);
             // box dims are limited to 256 elements (words) x 256 rows; offsets must fit 16 bits
-            fits = (long long)w16 * 16 * hh <= stage_bytes && w16 * 4 <= 256 && hh <= 256 && (long long)w16 * 16 * hh <= 65536 &&
-                   wx0 > -(1 << 24) && ry0 > -(1 << 24);
+            const bool shape_ok = w16 * 4 <= 256 && hh <= 256 && wx0 > -(1 << 24) && ry0 > -(1 << 24);
+            const long long bytes = (long long)w16 * 16 * hh;
+            fits = shape_ok && bytes <= stage_bytes;
+            if (!fits && shape_ok && r.g1 - r.g0 == 1) {       // a single strip: give it 2 or 4 frame-set slots of the stage
+              for (int m = 2; m <= 4 && !fits; m *= 2)
+                if (bytes <= (long long)m * stage_bytes && (long long)m * stage_bytes <= 65536) { fits = true; fs_bytes = m * stage_bytes; }
+            }
           }
           if (n_act && !fits && r.g1 - r.g0 > 1) {
             const int mid = (r.g0 + r.g1) / 2;
@@ -142,14 +170,42 @@ inline void build_tma_plan(int NC, int FW, int FH, int BW, int BH, bool nearest,
             continue;
           }
           if (n_act && fits) {
+            // pitch: among w16 .. w16+7 (while the box still fits) the one with the fewest bank wavefronts for this item's loads
+            int best_w = w16;
+            long long best_cost = -1;
+            for (int cand = w16; cand < w16 + 8; ++cand) {
+              if (cand != w16 && ((long long)cand * 16 * hh > fs_bytes || cand * 4 > 256 || menu_w16(cand) != cand)) continue;
+              long long cost = 0;
+              unsigned word[32];
+              for (int g = r.g0; g < r.g1; ++g)
+                for (int wv = 0; wv < 8; ++wv)
+                  for (int row = 0; row < 2; ++row)
+                    for (int wi = 0; wi < 3; ++wi) {
+                      int n = 0;
+                      for (int lane = 0; lane < 32; ++lane) {
+                        const Ent& e = ent[g * 256 + wv * 32 + lane];
+                        if (!e.active) continue;
+                        const int b = 3 * e.sx, w0 = floor_div(b, 4), sh = b - 4 * w0;
+                        if (wi == 2 && sh != 3) continue;
+                        word[n++] = (unsigned)((e.sy - ry0 + row) * (cand * 4) + (w0 - bx0) + wi);
+                      }
+                      cost += lds_wavefronts(word, n);
+                    }
+              if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_w = cand; }
+            }
+            w16 = best_w;
             int shape = -1;
             for (size_t s = 0; s < out.shapes.size(); ++s)
               if (out.shapes[s].x == w16 * 4 && out.shapes[s].y == hh) { shape = (int)s; break; }
             if (shape < 0) { shape = (int)out.shapes.size(); out.shapes.push_back(make_int2(w16 * 4, hh)); }
             it.shape = (unsigned short)shape; it.xw = bx0; it.y = ry0; it.tx_bytes = (unsigned)(w16 * 16 * hh);
+            it.fs_bytes = fs_bytes;
             out.box_bytes += it.tx_bytes;
+            item_cost += (long long)n_act * (4 * stage_bytes / fs_bytes == 4 ? 10 : (fs_bytes == 2 * stage_bytes ? 13 : 18));
           } else {
             it.flags |= ITEM_GATHER;
+            it.fs_bytes = stage_bytes;
+            item_cost += (long long)n_act * 80;
           }
           // entries of this range
           for (int i = r.g0 * 256; i < r.g1 * 256; ++i) {
@@ -179,7 +235,16 @@ inline void build_tma_plan(int NC, int FW, int FH, int BW, int BH, bool nearest,
         for (const TmaItem& it : made) { out.items.push_back(it); t.w++; }
       }
       out.tiles.push_back(t);
+      tile_cost.push_back(item_cost);
     }
+  // heavy tiles first: CTA c takes units c, c + G, c + 2G, ... of each frame-set group, so every CTA gets one tile of
+  // each cost stratum and the last round consists of the cheapest tiles
+  std::vector<int> order(out.tiles.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tile_cost[a] > tile_cost[b]; });
+  std::vector<int4> sorted(out.tiles.size());
+  for (size_t i = 0; i < order.size(); ++i) sorted[i] = out.tiles[order[i]];
+  out.tiles.swap(sorted);
 }
 
 // What one cp.async.bulk.tensor.3d of `shape` at (xw, y) of a frame delivers: the box, zero where it leaves the frame.

@@ -1,0 +1,89 @@
+// bevk_shard.cuh -- camera-per-GPU sharding of the BEV path: slab geometry and the compose kernel.
+//
+// The reference composes the four masked camera images with a cv2.add chain (SurroundBirdEyeView/surroundBEV.py:316-320).
+// A saturating sum of non-negative bytes does not depend on the order (min(min(a+b,255)+c,255) == min(a+b+c,255)), so
+// the chain can be cut anywhere: rank r renders only its cameras -- into a SLAB, the tile-aligned bounding box of the
+// union of their masks, 0.9-1.2 MB instead of the 3 MB canvas at 1000x1000 -- one all-gather moves the slabs over
+// NVLink, and every rank composes them.  k_compose_slabs is that compose (+ the car overlay, :323-324).
+#pragma once
+#include "bevk_bev.cuh"
+
+namespace bevk {
+
+constexpr int SHARD_MAX_RANKS = 8;
+
+struct SlabRect { int ox, oy, ox1, oy1; };   // canvas pixels [ox,ox1) x [oy,oy1); empty when ox1 <= ox
+
+// ranks' cameras: contiguous blocks, the first n_cam % world ranks get one more (cameracalibration_b200/sharding.py:block_range)
+inline void shard_block(int n, int rank, int world, int* lo, int* hi) {
+  const int base = n / world, extra = n % world;
+  *lo = rank * base + (rank < extra ? rank : extra);
+  *hi = *lo + base + (rank < extra ? 1 : 0);
+}
+
+// tile-aligned bounding box of the union of the masks of cameras [lo,hi), clipped to the canvas
+inline SlabRect slab_rect(const uint8_t* const* masks, int lo, int hi, int BW, int BH) {
+  int x0 = BW, y0 = BH, x1 = 0, y1 = 0;
+  for (int k = lo; k < hi; ++k)
+    for (int y = 0; y < BH; ++y) {
+      const uint8_t* row = masks[k] + (size_t)y * BW;
+      int a = 0, b = BW - 1;
+      while (a < BW && !row[a]) ++a;
+      if (a == BW) continue;
+      while (!row[b]) --b;
+      if (a < x0) x0 = a;
+      if (b + 1 > x1) x1 = b + 1;
+      if (y < y0) y0 = y;
+      y1 = y + 1;
+    }
+  SlabRect r{0, 0, 0, 0};
+  if (x1 <= x0 || y1 <= y0) return r;
+  r.ox = x0 / TILE * TILE; r.oy = y0 / TILE * TILE;
+  r.ox1 = (x1 + TILE - 1) / TILE * TILE; r.oy1 = (y1 + TILE - 1) / TILE * TILE;
+  if (r.ox1 > BW) r.ox1 = BW;
+  if (r.oy1 > BH) r.oy1 = BH;
+  return r;
+}
+
+struct ComposeArgs {
+  const uint8_t* slabs;            // [world][batch][slab_bytes]
+  long long slab_bytes;
+  int world, batch, BW, BH;
+  SlabRect rect[SHARD_MAX_RANKS];
+  const uint8_t* car;              // dense canvas or null
+  uint8_t* out;                    // [batch][BH][BW][3]
+};
+
+#ifdef __CUDACC__
+// grid (blocks, batch).  WORD: canvas rows are whole 32-bit words (BW % 4 == 0) and every slab edge falls on a word
+// boundary (tile-aligned x, or the canvas edge) -> 4 bytes per step; otherwise one byte per step.
+template <bool WORD>
+__global__ void __launch_bounds__(256) k_compose_slabs(ComposeArgs a) {
+  const int b = blockIdx.y;
+  const long long row_bytes = (long long)a.BW * 3, total = row_bytes * a.BH;
+  const long long n = WORD ? total / 4 : total;
+  uint8_t* out = a.out + (size_t)b * total;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long off = WORD ? i * 4 : i;
+    const int y = (int)(off / row_bytes), xb = (int)(off - (long long)y * row_bytes);
+    unsigned v = 0;
+#pragma unroll
+    for (int r = 0; r < SHARD_MAX_RANKS; ++r) {
+      if (r >= a.world) break;
+      const SlabRect q = a.rect[r];
+      if (y < q.oy || y >= q.oy1 || xb < q.ox * 3 || xb >= q.ox1 * 3) continue;
+      const uint8_t* p = a.slabs + ((size_t)r * a.batch + b) * a.slab_bytes + (size_t)(y - q.oy) * ((q.ox1 - q.ox) * 3) + (xb - q.ox * 3);
+      if (WORD) v = __vaddus4(v, __ldg(reinterpret_cast<const unsigned*>(p)));
+      else v = min(255u, v + __ldg(p));
+    }
+    if (a.car) {
+      if (WORD) v = __vaddus4(v, __ldg(reinterpret_cast<const unsigned*>(a.car + off)));
+      else v = min(255u, v + __ldg(a.car + off));
+    }
+    if (WORD) *reinterpret_cast<unsigned*>(out + off) = v;
+    else out[off] = (uint8_t)v;
+  }
+}
+#endif
+
+}  // namespace bevk

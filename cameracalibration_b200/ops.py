@@ -377,8 +377,10 @@ class BevEngine:
         frames: one uint8 CUDA array [batch][n_cam][FH][FW][3], or a list (batch) of lists (n_cam) of uint8
         CUDA arrays [FH][FW][3] -- anything exposing ``__cuda_array_interface__``, C-contiguous, on this
         engine's device.  car / out likewise ([BH][BW][3] / [batch][BH][BW][3]); without ``out`` a torch
-        tensor is allocated.  ``stream``: raw CUDA stream handle the work is enqueued on (default: the ctx
-        stream); the call does not synchronise.  Returns ``out``."""
+        tensor is allocated.  ``stream``: raw CUDA stream handle the work is enqueued on for THIS call; default torch's
+        current stream on the engine's device (so that torch kernels that produced ``frames``, this render and whatever
+        consumes ``out`` are ordered), or the ctx's own stream when torch is not in use.  The ctx goes back to its previous
+        stream afterwards.  The call does not synchronise.  Returns ``out``."""
         if not self.finalized:
             self.finalize()
         frame_shape = (self.FH, self.FW, 3)
@@ -401,11 +403,13 @@ class BevEngine:
             out = torch.empty((batch, self.BH, self.BW, 3), dtype=torch.uint8, device=torch.device("cuda", self.ctx.device))
         d_out = _cuda_ptr(out, (batch, self.BH, self.BW, 3))[0]
         d_car = _cuda_ptr(car, (self.BH, self.BW, 3))[0] if car is not None else None
-        if stream is not None:
-            self.ctx.set_stream(stream)
+        if stream is None:
+            from .sharding import _torch_current_stream
+            stream = _torch_current_stream(self.ctx.device)
         table = (C.c_void_p * len(ptrs))(*ptrs)
-        L.check(self.ctx.lib.bevk_bev_run_frames(self.ctx.h, table, batch, C.c_void_p(d_car), L.FLAG_BALANCE if balance else 0,
-                                                 C.c_void_p(d_out)))
+        with self.ctx.on_stream(stream):
+            L.check(self.ctx.lib.bevk_bev_run_frames(self.ctx.h, table, batch, C.c_void_p(d_car), L.FLAG_BALANCE if balance else 0,
+                                                     C.c_void_p(d_out)))
         return out
 
     def run_device_cams(self, d_srcs_ptr: int, batch: int, cam_lo: int, cam_hi: int, d_out_ptr: int):

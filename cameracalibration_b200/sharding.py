@@ -1,21 +1,26 @@
-"""Multi-GPU sharding of the BEV path: one process per GPU, torch.distributed for the plumbing.
+"""Multi-GPU sharding of the BEV path: one process per GPU.
 
-The reference is single-process (no collective anywhere); the path shards two ways:
+The reference is single-process (no collective anywhere); the path shards two ways, both implemented in
+libbevk.so (bevk_shard_* / bevk_bev_run_sharded, include/bevk.h) so that a binding without torch can use them too:
 
-  * frame-sets per GPU ("frames"): every rank renders its own block of frame-sets with a full
-    replica of the (8 MB) LUT.  No data-path collective; an optional all-gather only if every
-    rank must end up with every canvas.
-  * cameras per GPU ("cameras"): rank r renders the masked, weighted partial canvas of its
-    cameras only (bevk_bev_run_device_cams), ONE all-gather moves the partial canvases over
-    NVLink, and each rank composes them with the saturating sum (bevk_sat_sum_device).  The
-    compose is exact because cv2.add's saturation is order-independent on this path (blend
-    weights sum to <= 255; plain seams overlap at most pairwise -- SURVEY 8a row a10), which
-    tests/test_sharding_gloo.py checks against the reference's result.  balance=True is not available in
-    this mode (it needs the per-camera V sums before the warp).
+  * frame-sets per GPU ("frames"): every rank renders its own block of frame-sets with a full replica of the plan.
+    No data-path collective.
+  * cameras per GPU ("cameras"): rank r renders cameras [lo_r, hi_r) of every frame-set into a SLAB (the tile-aligned
+    bounding box of the union of their masks: 0.9-1.2 MB per frame-set at 1000x1000 instead of the 3 MB canvas), ONE
+    ncclAllGather moves the slabs over NVLink, and every rank composes them with the saturating sum.  Exact, because
+    the reference's cv2.add chain (surroundBEV.py:316-320) is order-independent.  balance=True is not available in
+    this mode (luminance_balance needs every camera's V mean before the warp).
 
-The pure partition functions below are what the world_size-2 gloo tests exercise on CPU.
+ShardedBev is a thin caller: it carries the NCCL unique id between the ranks with torch.distributed (any backend) and
+points the engine at torch's current stream for the duration of a call, so that frames produced by torch kernels,
+the render, the collective and the consumer of ``out`` are ordered on ONE stream.
+
+The pure partition functions below are what the world_size-2 gloo tests exercise on CPU; libbevk.so uses the same rule
+(bevk_shard.cuh: shard_block), and the GPU tests compare the two.
 """
 from __future__ import annotations
+
+import ctypes as C
 
 
 def block_range(n_items: int, rank: int, world: int) -> tuple[int, int]:
@@ -30,23 +35,67 @@ def block_range(n_items: int, rank: int, world: int) -> tuple[int, int]:
 
 def camera_range(n_cam: int, rank: int, world: int) -> tuple[int, int]:
     """Cameras of one rank.  With more ranks than cameras the trailing ranks get an empty range
-    (they still join the all-gather with an all-zero partial canvas)."""
+    (they still join the all-gather, with an empty slab)."""
     return block_range(n_cam, rank, world)
 
 
-class ShardedBev:
-    """Drives a BevEngine under torch.distributed.  Tensors are torch CUDA tensors; the engine
-    only sees their device pointers."""
+def slab_rect(masks, lo: int, hi: int, tile: int = 32):
+    """Tile-aligned bounding box (x0, y0, x1, y1) of the union of masks[lo:hi], clipped to the canvas; (0, 0, 0, 0)
+    when empty.  NumPy statement of bevk_shard.cuh:slab_rect."""
+    import numpy as np
+    if hi <= lo:
+        return 0, 0, 0, 0
+    u = np.zeros_like(np.asarray(masks[lo]), dtype=bool)
+    for m in masks[lo:hi]:
+        u |= np.asarray(m) != 0
+    if not u.any():
+        return 0, 0, 0, 0
+    ys, xs = np.nonzero(u.any(axis=1))[0], np.nonzero(u.any(axis=0))[0]
+    BH, BW = u.shape
+    x0, y0 = int(xs[0]) // tile * tile, int(ys[0]) // tile * tile
+    x1 = min(BW, (int(xs[-1]) + tile) // tile * tile)
+    y1 = min(BH, (int(ys[-1]) + tile) // tile * tile)
+    return x0, y0, x1, y1
 
-    def __init__(self, engine, policy: str = "frames", group=None):
-        import torch.distributed as dist
+
+class ShardedBev:
+    """Drives a BevEngine under a multi-process launch.  Tensors are CUDA arrays (torch or anything with
+    ``__cuda_array_interface__``); the engine only sees their device pointers."""
+
+    def __init__(self, engine, policy: str = "frames", group=None, rank: int | None = None, world: int | None = None,
+                 connect: bool = True):
+        from . import _lib as L
         if policy not in ("frames", "cameras"):
             raise ValueError("policy must be 'frames' or 'cameras'")
         self.e, self.policy, self.group = engine, policy, group
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self._parts = None
-        self._mine = None
+        if rank is None or world is None:
+            import torch.distributed as dist
+            on = dist.is_available() and dist.is_initialized()
+            rank = dist.get_rank(group) if on else 0
+            world = dist.get_world_size(group) if on else 1
+        self.rank, self.world = int(rank), int(world)
+        if not engine.finalized:
+            engine.finalize()
+        lib, h = engine.ctx.lib, engine.ctx.h
+        L.check(lib.bevk_shard_configure(h, L.SHARD_CAMERAS if policy == "cameras" else L.SHARD_FRAMES, self.rank, self.world))
+        if policy == "cameras" and self.world > 1 and connect:   # connect=False: geometry / render_slabs / compose only
+            self._connect()
+
+    def _connect(self):
+        """NCCL unique id: made on rank 0, carried to the others as a tensor broadcast (works on gloo and nccl)."""
+        import torch
+        import torch.distributed as dist
+        from . import _lib as L
+        lib, h = self.e.ctx.lib, self.e.ctx.h
+        buf = (C.c_uint8 * 128)()
+        if self.rank == 0:
+            L.check(lib.bevk_shard_unique_id(buf, 128))
+        backend = dist.get_backend(self.group)
+        dev = torch.device("cuda", self.e.ctx.device) if backend == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        raw = bytes(t.cpu().tolist())
+        L.check(lib.bevk_shard_connect(h, raw, 128))
 
     def my_frame_sets(self, n_sets: int):
         return block_range(n_sets, self.rank, self.world)
@@ -54,36 +103,72 @@ class ShardedBev:
     def my_cameras(self):
         return camera_range(self.e.n_cam, self.rank, self.world)
 
-    def render(self, frame_ptrs, batch: int, out, car=None, balance: bool = False):
-        """frame_ptrs: int64 CUDA tensor [batch * n_cam] of device pointers (for policy
-        'cameras' every rank passes the full table but only its cameras' entries are read).
-        out: uint8 CUDA tensor [batch, BH, BW, 3].  Only enqueues work on the engine's stream
-        (plus the collective on torch's current stream for 'cameras')."""
-        import torch
-        import torch.distributed as dist
+    def info(self, rank: int | None = None):
+        """(cam_lo, cam_hi, (x0, y0, x1, y1), slab_bytes) of `rank` as libbevk.so computed them."""
+        from . import _lib as L
+        lo, hi, sb = C.c_int(), C.c_int(), C.c_int64()
+        rect = (C.c_int32 * 4)()
+        L.check(self.e.ctx.lib.bevk_shard_info(self.e.ctx.h, self.rank if rank is None else rank, C.byref(lo), C.byref(hi), rect, C.byref(sb)))
+        return lo.value, hi.value, tuple(rect), sb.value
+
+    def render(self, frames, out, car=None, balance: bool = False, stream: int | None = None):
+        """frames: uint8 CUDA array [batch][n_cam][FH][FW][3] (a frame stack; with policy 'cameras' every rank passes
+        the same batch and only its own cameras' frames are read).  out: uint8 CUDA array [batch][BH][BW][3].
+        ``stream``: raw CUDA stream handle; default torch's current stream.  Only enqueues; returns ``out``."""
+        from . import _lib as L
+        from .ops import _cuda_ptr
         e = self.e
-        carp = 0 if car is None else car.data_ptr()
-        if self.policy == "frames" or self.world == 1:
-            e.run_device(frame_ptrs.data_ptr(), batch, out.data_ptr(), carp, balance)
-            return out
-        if balance:
-            raise ValueError("balance=True is not supported with camera sharding")
-        lo, hi = self.my_cameras()
-        n = out.numel()
-        if self._parts is None or self._parts.numel() != n * self.world:
-            self._parts = torch.empty((self.world, n), dtype=torch.uint8, device=out.device)
-            self._mine = torch.empty((n,), dtype=torch.uint8, device=out.device)
-        e.run_device_cams(frame_ptrs.data_ptr(), batch, lo, hi, self._mine.data_ptr())
-        dist.all_gather_into_tensor(self._parts.view(-1), self._mine, group=self.group)
-        # the all-gather carries every rank's partial canvas; compose locally (8 partials per call)
-        ptrs = [self._parts[r].data_ptr() for r in range(self.world)]
-        while len(ptrs) > 8:   # bevk_sat_sum_device takes up to 8 inputs: fold the rest pairwise
-            head, ptrs = ptrs[:8], ptrs[8:]
-            e.sat_sum_device(head, n, self._parts[0].data_ptr(), 0)
-            ptrs = [self._parts[0].data_ptr()] + ptrs
-        e.sat_sum_device(ptrs, n, out.data_ptr(), 0)
-        if car is not None:   # car overlay, tiled over the batch
-            per = n // batch
-            for b in range(batch):
-                e.sat_sum_device([out.data_ptr() + b * per], per, out.data_ptr() + b * per, carp)
+        base, shape = _cuda_ptr(frames, None)
+        if len(shape) != 5 or tuple(shape[1:]) != (e.n_cam, e.FH, e.FW, 3):
+            raise L.BevkError(f"frames must be uint8[batch][{e.n_cam}][{e.FH}][{e.FW}][3], got {tuple(shape)}")
+        batch = shape[0]
+        d_out = _cuda_ptr(out, (batch, e.BH, e.BW, 3))[0]
+        d_car = _cuda_ptr(car, (e.BH, e.BW, 3))[0] if car is not None else None
+        if stream is None:
+            stream = _torch_current_stream(e.ctx.device)
+        with e.ctx.on_stream(stream):
+            L.check(e.ctx.lib.bevk_bev_run_sharded(e.ctx.h, C.c_void_p(base), e.FH * e.FW * 3, batch, C.c_void_p(d_car),
+                                                   L.FLAG_BALANCE if balance else 0, C.c_void_p(d_out)))
         return out
+
+    def slab_buffer(self, batch: int):
+        """torch uint8 CUDA tensor [world][batch][slab_bytes] for render_slabs / compose."""
+        import torch
+        return torch.zeros((self.world, batch, self.info()[3]), dtype=torch.uint8, device=torch.device("cuda", self.e.ctx.device))
+
+    def render_slabs(self, frames, as_rank: int, slabs, stream: int | None = None):
+        """The render half of the 'cameras' policy on its own: the slabs of rank `as_rank` into slabs[as_rank]."""
+        from . import _lib as L
+        from .ops import _cuda_ptr
+        e = self.e
+        base, shape = _cuda_ptr(frames, None)
+        d_slabs = _cuda_ptr(slabs, (self.world, shape[0], self.info()[3]))[0]
+        with e.ctx.on_stream(_torch_current_stream(e.ctx.device) if stream is None else stream):
+            L.check(e.ctx.lib.bevk_shard_render(e.ctx.h, C.c_void_p(base), e.FH * e.FW * 3, shape[0], int(as_rank), C.c_void_p(d_slabs)))
+
+    def compose(self, slabs, out, car=None, stream: int | None = None):
+        """The compose half: slabs[world][batch][slab_bytes] (+ car) -> out[batch][BH][BW][3]."""
+        from . import _lib as L
+        from .ops import _cuda_ptr
+        e = self.e
+        d_slabs, shape = _cuda_ptr(slabs, None)
+        d_out = _cuda_ptr(out, (shape[1], e.BH, e.BW, 3))[0]
+        d_car = _cuda_ptr(car, (e.BH, e.BW, 3))[0] if car is not None else None
+        with e.ctx.on_stream(_torch_current_stream(e.ctx.device) if stream is None else stream):
+            L.check(e.ctx.lib.bevk_shard_compose(e.ctx.h, C.c_void_p(d_slabs), shape[1], C.c_void_p(d_car), C.c_void_p(d_out)))
+        return out
+
+    def link_bytes(self) -> int:
+        """Bytes this rank received over NVLink in the last render()."""
+        return int(self.e.ctx.lib.bevk_shard_last_link_bytes(self.e.ctx.h))
+
+
+def _torch_current_stream(device: int):
+    """torch's current stream on `device` as a raw handle, or None (= the ctx's own stream) without torch."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return torch.cuda.current_stream(device).cuda_stream
+    except Exception:
+        pass
+    return None

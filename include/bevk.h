@@ -186,6 +186,34 @@ int bevk_bev_last_path(bevk_ctx *ctx);
  * 16 bytes, or BEVK_TMA=0). */
 int bevk_bev_tma_plan_info(bevk_ctx *ctx, int64_t *n_items, int64_t *n_shapes, int64_t *box_bytes, int64_t *tma_entries,
                            int64_t *gather_entries);
+/* ---- multi-GPU sharding: one process (one ctx) per GPU ---------------------------------------------------
+ * The reference is a single process (no collective anywhere); the path shards two ways:
+ *   BEVK_SHARD_FRAMES   every rank renders its own frame-sets with a replica of the plan -- no exchange at all;
+ *   BEVK_SHARD_CAMERAS  rank r renders cameras [lo_r, hi_r) (contiguous blocks) of EVERY frame-set into a slab -- the
+ *                       tile-aligned bounding box of the union of their masks -- ONE ncclAllGather moves the slabs
+ *                       over NVLink, and each rank composes them with the saturating sum, which is exact because
+ *                       the cv2.add chain of BevGenerator.__call__ (surroundBEV.py:316-320) is order-independent.
+ * NCCL is dlopen'ed (libnccl.so.2) on first use.  Call order: bevk_bev_finalize, bevk_shard_configure on every rank,
+ * bevk_shard_unique_id on ONE rank, its 128 bytes carried to the others by the launcher (file, MPI, torch.distributed),
+ * bevk_shard_connect on every rank, then bevk_bev_run_sharded per step.  All work is enqueued on the ctx stream. */
+enum { BEVK_SHARD_FRAMES = 0, BEVK_SHARD_CAMERAS = 1 };
+int bevk_shard_configure(bevk_ctx *ctx, int policy, int rank, int world);
+int bevk_shard_unique_id(void *id128, int len);
+int bevk_shard_connect(bevk_ctx *ctx, const void *id128, int len);
+/* Partition and slab geometry of `rank`: its cameras [cam_lo, cam_hi), its slab rectangle {x0, y0, x1, y1} in canvas
+ * pixels, and the (padded, equal for all ranks) bytes of one frame-set's slab. */
+int bevk_shard_info(bevk_ctx *ctx, int rank, int *cam_lo, int *cam_hi, int32_t rect[4], int64_t *slab_bytes);
+/* BevGenerator.__call__ over a frame stack (see bevk_bev_run_stack) under the configured policy.  CAMERAS: every rank
+ * passes the same batch; only the frames of its own cameras are read; every rank ends with all canvases in d_out. */
+int bevk_bev_run_sharded(bevk_ctx *ctx, const void *d_frames, int64_t frame_stride, int batch, const void *d_car, int flags,
+                         void *d_out);
+/* Bytes this rank received over NVLink in the last bevk_bev_run_sharded call. */
+int64_t bevk_shard_last_link_bytes(bevk_ctx *ctx);
+/* The two halves of the CAMERAS policy on their own (tests, custom exchanges): render the slabs of rank `as_rank`
+ * into d_slabs[as_rank][batch][slab_bytes]; compose d_slabs[world][batch][slab_bytes] (+ car) into canvases. */
+int bevk_shard_render(bevk_ctx *ctx, const void *d_frames, int64_t frame_stride, int batch, int as_rank, void *d_slabs);
+int bevk_shard_compose(bevk_ctx *ctx, const void *d_slabs, int batch, const void *d_car, void *d_out);
+
 /* ---- CUDA graphs over the device-pointer entry points ------------------------------------------------
  * Everything the "_device" / "_stack" / "_frames" entry points enqueue on the ctx stream between begin and end is
  * captured (stream capture) instead of executed, instantiated once, and replayed `times` times by one call --

@@ -283,7 +283,7 @@ static int mode_bev(const char* in_path, const char* out_path, int tma_stage_byt
       for (int k = 0; k < NC; ++k) { p1[k] = m1[k].data(); p2[k] = m2[k].data(); pm[k] = mk[k].data(); }
       build_tma_plan(NC, FW, FH, BW, BH, nearest != 0, p1.data(), p2.data(), pm.data(), tma_stage_bytes, true, tp);
     }
-    std::vector<uint8_t> stage((size_t)tma_stage_bytes + 16, 0xEE);
+    std::vector<uint8_t> stage((size_t)4 * tma_stage_bytes + 16, 0xEE);   // one ring slot = 4 FS
     for (const int4& tile : tp.tiles) {
       unsigned acc[ACC_WORDS];
       for (auto& a : acc) a = 0xdeadbeefu;                 // every word must be written before the write-out reads it
@@ -296,7 +296,9 @@ static int mode_bev(const char* in_path, const char* out_path, int tma_stage_byt
         if (!gather) {
           memset(stage.data(), 0xEE, stage.size());
           const int2 shape = tp.shapes[item.shape];
-          CHECK((unsigned)(shape.x * 4 * shape.y) == item.tx_bytes && (int)item.tx_bytes <= tma_stage_bytes, "box bytes");
+          CHECK((unsigned)(shape.x * 4 * shape.y) == item.tx_bytes && (int)item.tx_bytes <= item.fs_bytes, "box bytes");
+          CHECK(item.fs_bytes == tma_stage_bytes || ((item.fs_bytes == 2 * tma_stage_bytes || item.fs_bytes == 4 * tma_stage_bytes) &&
+                                                     item.k1 - item.k0 == 1), "frame-set slot size");
           CHECK((item.xw & 3) == 0 && (shape.x & 3) == 0, "box alignment");
           model_tma_box(src, FW, FH, shape, item.xw, item.y, stage.data());
         }

@@ -376,6 +376,36 @@ def test_device_resident_and_camera_sharded_compose(ops, fx):
     assert e.ctx.launches > 0
 
 
+def test_undistorter_slots_are_owned(ops, fx):
+    """A bevk_ctx has 8 undistorter slots: each live Undistorter owns one, a 9th on an explicit ctx raises, closing one
+    frees its slot, and on the shared default ctx the 9th gets a context of its own; a call whose destination was sized
+    for another map is refused by the library instead of writing past it."""
+    import ctypes as Ct
+    from cameracalibration_b200 import _lib as L
+    K, D, _ = fx.calib["front"]
+    P = C.dst_camera_matrix(K, 1280, 1024, 1, 1)
+    ctx = L.Context(0)
+    img = fx.img("front")
+    us = [ops.Undistorter(K, D, P, (320 + 16 * i, 256), ctx=ctx) for i in range(8)]
+    assert sorted(u.slot for u in us) == list(range(8))
+    with pytest.raises(L.BevkError, match="8 undistorter slots"):
+        ops.Undistorter(K, D, P, (320, 256), ctx=ctx)
+    want0 = us[0](img)
+    us[3].close()
+    with pytest.raises(L.BevkError, match="closed"):
+        us[3](img)
+    u9 = ops.Undistorter(K, D, P, (640, 512), ctx=ctx)
+    assert u9.slot == 3 and u9(img).shape == (512, 640, 3)
+    assert (us[0](img) == want0).all()                       # nobody else's map was touched
+    out = np.empty((256, 320, 3), np.uint8)
+    rc = ctx.lib.bevk_undistort(ctx.h, 3, L.vptr(img), 1280, 1024, 3840, 3, L.vptr(out), 320, 256, 960, 1)
+    assert rc != 0 and b"holds a 640x512 map" in ctx.lib.bevk_last_error()
+    d = L.default_context()
+    keep = [ops.Undistorter(K, D, P, (320, 256)) for _ in range(9)]
+    assert sum(u.ctx is d for u in keep) <= 8 and any(u.ctx is not d for u in keep)
+    assert all((u(img) == keep[0](img)).all() for u in keep[1:])
+
+
 def test_errors_are_loud(ops, fx):
     from cameracalibration_b200 import BevkError
     e = ops.BevEngine(4, (64, 48), (40, 40))

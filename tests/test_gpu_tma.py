@@ -206,3 +206,45 @@ def test_tma_falls_back_when_the_stack_is_not_16_byte_friendly(ops, fx):
     F2 = fx.frames(g2.FW, g2.FH)
     ref = C.RefBev(fx.scaled_calib(g2), g2, True, False, masks=masks2)
     assert (e2.run([F2])[0] == ref(*F2)).all() and e2.last_path() == "gather"
+
+
+def test_cuda_graph_capture_of_the_device_entry_points(ops, fx):
+    """bevk_graph_begin / end / launch: one frame-set batch (plain and BALANCE: memsets + five kernels) captured once and
+    replayed; the replay on new frame contents gives what the direct call gives, and launches are counted per replay."""
+    import torch
+    from cameracalibration_b200 import _lib as L
+    g = fx.geometry()
+    et, _ = _engine(ops, fx, g, True, calib=fx.calib)
+    dev = torch.device("cuda", et.ctx.device)
+    F = fx.frames()
+    d_all = _stack(torch, dev, [F, F[::-1], F, F, F[::-1]])
+    car = torch.from_numpy(fx.car()).to(dev)
+    for balance in (False, True):
+        want = _run_stack(torch, et, d_all, car, balance)                   # also warms every buffer and table
+        out = torch.zeros((5, g.BH, g.BW, 3), dtype=torch.uint8, device=dev)
+        with et.ctx.graph_capture() as gr:
+            et.run_stack(d_all.data_ptr(), g.FH * g.FW * 3, 5, out.data_ptr(), car.data_ptr(), balance)
+        et.ctx.sync()
+        assert not out.any().item()                                          # capturing executes nothing
+        n0 = et.ctx.launches
+        gr.launch(3)
+        et.ctx.sync()
+        assert et.ctx.launches - n0 == 3 * (5 if balance else 1)
+        assert (out.cpu().numpy() == want).all()
+        d_all.copy_(d_all.flip(0))                                           # same buffers, new contents
+        torch.cuda.synchronize()
+        gr.launch()
+        et.ctx.sync()
+        assert (out.cpu().numpy() == want[::-1]).all() if not balance else h16(out.cpu().numpy()[4]) == h16(want[0])
+        d_all.copy_(d_all.flip(0))
+        torch.cuda.synchronize()
+        gr.destroy()
+    # a call that has to build something inside the capture is reported, not silently dropped
+    e2, _ = _engine(ops, fx, fx.geometry(640, 512, 500, 500), True)
+    d2 = torch.zeros((1, 4, 512, 640, 3), dtype=torch.uint8, device=dev)
+    o2 = torch.empty((1, 500, 500, 3), dtype=torch.uint8, device=dev)
+    with pytest.raises(L.BevkError):
+        with e2.ctx.graph_capture():
+            e2.run_stack(d2.data_ptr(), 512 * 640 * 3, 1, o2.data_ptr())   # first call: tensor maps are built here
+    e2.run_stack(d2.data_ptr(), 512 * 640 * 3, 1, o2.data_ptr())            # the ctx is usable afterwards
+    e2.ctx.sync()

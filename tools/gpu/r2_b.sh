@@ -1,0 +1,22 @@
+#!/bin/bash
+# round 2, call B: multi-pass items / deeper ring / pitch selection / cost-sorted tiles; configuration sweep
+cd "$GRAFT_REPO_ROOT" || exit 1
+O=gpurun_out/r2b; mkdir -p $O
+echo "== tma tests"
+timeout 900 python -m pytest tests/test_gpu_tma.py -x -q 2>&1 | tail -15 | tee $O/pytest_tma.log
+echo "== config sweep (device-resident value only)"
+for cfg in 6144,3 6144,2 4096,3 4096,4 8192,2; do
+  BEVK_TMA_CFG=$cfg BEVK_BENCH_NO_API=1 timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --e2e-steps 2 > $O/bench_$cfg.json 2> $O/bench_$cfg.err
+  python - "$O/bench_$cfg.json" "$cfg" <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(sys.argv[2], "ms/step", round(d["ms_per_step"],4), "frac", round(d["roofline"]["frac"],4), "isolated", round(d["roofline"]["kernel_ms_isolated"],4), d["plan"]["tma"], d["e2e"]["matches_device_path"])
+except Exception as e:
+    print(sys.argv[2], "FAILED", e)
+PY
+done
+echo "== ncu full capture of the default config"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_bev_tma -s 5 -c 1 -o $O/prof_tma python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $O/b_ncu2.log 2>&1
+BEVK_TMA_CFG=6144,2 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_bev_tma -s 5 -c 1 -o $O/prof_tma_6144_2 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $O/b_ncu3.log 2>&1
+ls -la $O
