@@ -36,6 +36,9 @@ ALT_WORKLOADS = {   # BASELINE.json configs[1..3] shapes (all 4 cameras, batch f
     "cfg4": {},
     "cfg2": dict(FW=1280, FH=960, BW=1000, BH=1000, blend=False, balance=False),
     "cfg3": dict(FW=1920, FH=1080, BW=1200, BH=1200, blend=True, balance=True),
+    # BASELINE configs[4]: 8 cameras 3840x2160 -> 2000x2000, one camera per GPU on 8 GPUs (cameras 4-7 are
+    # the four fixtures with H rotated by 45 degrees about the canvas centre, 8 angular wedge masks)
+    "cfg5": dict(FW=3840, FH=2160, BW=2000, BH=2000, n_cam=8, batch=8, blend=False, balance=False),
 }
 NAMES = ("front", "back", "left", "right")
 
@@ -74,23 +77,45 @@ def dst_matrix(K, FW, FH, FS=1.0, SS=2.0):
     return P
 
 
-def build_engine(w, device):
-    from cameracalibration_b200 import _lib as L
-    from cameracalibration_b200 import ops
+def rig(w):
+    """(cameras [(K, D, H)], masks) of the workload: the four fixture cameras with the reference's masks, or the
+    8-camera rig of BASELINE configs[4]."""
+    import cv2
     from cameracalibration_b200.SurroundBirdEyeView import surroundBEV as S
     calib = synthetic_calibration(w["FW"], w["FH"], w["BW"], w["BH"])
     g = S._Geo()
     g.FW, g.FH, g.BW, g.BH = w["FW"], w["FH"], w["BW"], w["BH"]
     g.CW, g.CH = int(250 * w["BW"] / 1000), int(400 * w["BH"] / 1000)
+    cams = [calib[n] for n in NAMES]
+    if w["n_cam"] == 8:
+        c, s_ = np.cos(np.pi / 4), np.sin(np.pi / 4)
+        cx, cy = g.BW / 2, g.BH / 2
+        rot = np.array([[c, -s_, cx - c * cx + s_ * cy], [s_, c, cy - s_ * cx - c * cy], [0, 0, 1.0]])
+        cams = cams + [(K, D, rot @ H) for K, D, H in cams]
+        ang = np.linspace(0, 2 * np.pi, 9)
+        masks = []
+        for i in range(8):
+            tri = np.array([[cx, cy], [cx + g.BW * np.cos(ang[i]), cy + g.BW * np.sin(ang[i])],
+                            [cx + g.BW * np.cos(ang[i + 1]), cy + g.BW * np.sin(ang[i + 1])]]).astype(np.int32)
+            masks.append(cv2.fillPoly(np.zeros((g.BH, g.BW), np.uint8), [tri], 255))
+        return cams, masks, g, calib
+    return cams, None, g, calib
+
+
+def build_engine(w, device):
+    from cameracalibration_b200 import _lib as L
+    from cameracalibration_b200 import ops
+    from cameracalibration_b200.SurroundBirdEyeView import surroundBEV as S
+    cams, masks, g, calib = rig(w)
     ctx = L.Context(device)
     eng = ops.BevEngine(w["n_cam"], (g.FW, g.FH), (g.BW, g.BH), ctx=ctx)
-    if w["blend"]:
-        polys = np.stack([S._fill(S._blend_points(n, g), g) for n in NAMES])
-        masks = list(eng.blend_masks(polys, S._seam_lines(g)))
-    else:
-        masks = [S._fill(S._plain_points(n, g), g) for n in NAMES]
-    for i, n in enumerate(NAMES):
-        K, D, H = calib[n]
+    if masks is None:
+        if w["blend"]:
+            polys = np.stack([S._fill(S._blend_points(n, g), g) for n in NAMES])
+            masks = list(eng.blend_masks(polys, S._seam_lines(g)))
+        else:
+            masks = [S._fill(S._plain_points(n, g), g) for n in NAMES]
+    for i, (K, D, H) in enumerate(cams):
         eng.set_camera(i, K, D, dst_matrix(K, g.FW, g.FH), g.und_size, H)
         eng.set_mask(i, masks[i])
     eng.finalize()
@@ -227,7 +252,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=WORKLOAD["batch"])
+    ap.add_argument("--batch", type=int, default=0, help="frame-sets per GPU per step (default: the workload's own)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (default: min(steps, 20))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard", default="frames", choices=["frames", "cameras"],
@@ -237,22 +262,27 @@ def main():
                     help="cfg4 (default) is the headline; the others are secondary measurements of BASELINE configs")
     a = ap.parse_args()
     w = dict(WORKLOAD, **ALT_WORKLOADS[a.workload])
-    w["batch"] = a.batch
+    if a.batch:
+        w["batch"] = a.batch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     metric, unit = "surround_bev_frame_sets_per_sec", "frame-sets/s"
-    config = {"workload": f"{w['batch']} frame-sets/GPU x 4 cams {w['FW']}x{w['FH']} BGR -> {w['BW']}x{w['BH']} BEV, "
+    config = {"workload": f"{w['batch']} frame-sets/GPU x {w['n_cam']} cams {w['FW']}x{w['FH']} BGR -> {w['BW']}x{w['BH']} BEV, "
                           f"blend={w['blend']} balance={w['balance']} (BASELINE {a.workload} shape)",
               "sharding": ("frame-sets per GPU, no data-path collective" if a.shard == "frames" else
                            "cameras per GPU: each rank renders its cameras' slabs (tile-aligned mask bounding boxes), ONE "
                            "ncclAllGather of the slabs per step over NVLink, local saturating compose; every rank ends with all canvases"),
               "launch": "one step captured as a CUDA graph, the K timed steps replayed by one bevk_graph_launch call",
-              "l2": f"inputs ({w['batch'] * 4 * w['FW'] * w['FH'] * 3 / 1e6:.0f} MB/step) larger than L2; "
+              "l2": f"inputs ({w['batch'] * w['n_cam'] * w['FW'] * w['FH'] * 3 / 1e6:.0f} MB/step) larger than L2; "
                     "the frame-invariant LUT stays L2-resident by design"}
 
     if a.impl == "reference":
         if rank != 0:
+            return 0
+        if w["n_cam"] != 4:
+            print(json.dumps({"impl": "reference", "unavailable": "the reference (surroundBEV.py:285-294) is hard-wired to 4 cameras; "
+                                                                 "cfg5 has no reference arm, its oracle is per-camera raw2bev + N-way compose (tests/)"}))
             return 0
         calib = synthetic_calibration(w["FW"], w["FH"], w["BW"], w["BH"])
         from oracle import cv2_path as C
@@ -416,7 +446,7 @@ def main():
 
     # ---- the reference's own call: BevGenerator.__call__(front, back, left, right), one frame-set, NumPy in / NumPy out
     e2e_api = None
-    if rank == 0 and not os.environ.get("BEVK_BENCH_NO_API"):
+    if rank == 0 and not os.environ.get("BEVK_BENCH_NO_API") and nc == 4:
         from cameracalibration_b200.SurroundBirdEyeView import surroundBEV as S
         ar = S.BevGenerator.get_args()
         saved = {k: getattr(ar, k) for k in ("FRAME_WIDTH", "FRAME_HEIGHT", "BEV_WIDTH", "BEV_HEIGHT", "CAR_WIDTH", "CAR_HEIGHT")}
@@ -483,7 +513,7 @@ def main():
                              "algorithmic_bytes_per_frame_set": {"source_unique_32B_sectors": src_b, "canvas_write": canvas_b}},
                 "link_bytes_per_step": sharded.link_bytes() if cams else 0,
                 "clocks": sampler.summary(), "plan": dict(eng.plan_info(), tma=eng.tma_plan_info(), path=path_used)}
-        if not a.no_cpu_baseline and world == 1:
+        if not a.no_cpu_baseline and world == 1 and nc == 4:
             v, cores, sample = cpu_reference(w, calib, masks, n_sets=4, repeats=100000, seconds_cap=20.0)
             line["cpu_baseline"] = {"value": v, "unit": unit, "cores": cores, "kind": "port",
                                     "sample": sample + f"; os.cpu_count()={os.cpu_count()}",

@@ -69,6 +69,8 @@ SIGNATURES = {
     "bevk_shard_last_link_bytes": (C.c_int64, [_p]),
     "bevk_shard_render": (C.c_int, [_p, _p, C.c_int64, C.c_int, C.c_int, _p]),
     "bevk_shard_compose": (C.c_int, [_p, _p, C.c_int, _p, _p]),
+    "bevk_jpeg_decode": (C.c_int, [_p, C.POINTER(_p), C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int, _p, C.c_int64]),
+    "bevk_bev_run_jpeg": (C.c_int, [_p, C.POINTER(_p), C.POINTER(C.c_uint64), C.c_int, _p, C.c_int, _p]),
     "bevk_graph_begin": (C.c_int, [_p]),
     "bevk_graph_end": (C.c_int, [_p, C.POINTER(C.c_int)]),
     "bevk_graph_launch": (C.c_int, [_p, C.c_int, C.c_int]),
@@ -259,3 +261,34 @@ def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
     buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
     weakref.finalize(buf, _free_pinned, p.value)     # numpy keeps `buf` alive as the base of the array and its views
     return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+class PinnedPool:
+    """Recycling allocator of page-locked result arrays.  The reference returns a freshly allocated ndarray from every
+    call (the caller owns it); a pageable result makes the driver stage the device->host copy through its own bounce
+    buffer.  get(shape) hands out a page-locked array instead; when the caller drops it (and every view of it), the
+    buffer goes back to the pool rather than to cudaFreeHost, so a steady stream of calls allocates nothing."""
+
+    def __init__(self, keep: int = 8):
+        self.keep, self.free = keep, {}
+
+    def get(self, shape, dtype=np.uint8) -> np.ndarray:
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        stack = self.free.setdefault(n, [])
+        if stack:
+            buf, addr = stack.pop()
+        else:
+            p = _p()
+            check(load().bevk_host_alloc(n, C.byref(p)))
+            addr = p.value
+            buf = (C.c_uint8 * max(n, 1)).from_address(addr)
+        flat = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape)))
+        weakref.finalize(flat, self._give_back, n, buf, addr)    # every view (reshape, out[0], slices) has `flat` as its base
+        return flat.reshape(shape)
+
+    def _give_back(self, n, buf, addr):
+        stack = self.free.setdefault(n, [])
+        if len(stack) < self.keep:
+            stack.append((buf, addr))
+        else:
+            _free_pinned(addr)

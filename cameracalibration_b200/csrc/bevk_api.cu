@@ -30,12 +30,13 @@
 
 using namespace bevk;
 
-// k_bev_tma configurations built into the library: FS = bytes of one frame-set's staged source box (a ring slot is 4 FS),
-// STAGES = ring slots, MINCTAS = resident CTAs per SM the register budget is set for.  The first entry is the default;
-// BEVK_TMA_CFG="<FS>,<STAGES>" (read at bevk_bev_finalize) selects another one for tuning runs.
-#define BEVK_TMA_CONFIGS(X) X(6144, 3, 2) X(6144, 2, 3) X(4096, 3, 3) X(4096, 4, 2) X(8192, 2, 2)
-struct TmaConfig { int fs, stages, min_ctas; };
-#define X(FS, ST, MC) {FS, ST, MC},
+// k_bev_tma configurations built into the library: FS = bytes of one frame-set's staged source box (a ring slot holds 4 FS
+// of boxes), STAGES = ring slots, MINCTAS = resident CTAs per SM the register budget is set for, EG = LUT-entry groups per
+// slot (the plan's items never span more).  The first entry is the default; BEVK_TMA_CFG="<FS>,<STAGES>,<EG>" (read at
+// bevk_bev_finalize) selects another one for tuning runs.
+#define BEVK_TMA_CONFIGS(X) X(4096, 3, 2, 2) X(6144, 2, 2, 2) X(4096, 2, 3, 2) X(4096, 2, 2, 4) X(5120, 3, 2, 2)
+struct TmaConfig { int fs, stages, min_ctas, eg; };
+#define X(FS, ST, MC, EG) {FS, ST, MC, EG},
 static const TmaConfig kTmaConfigs[] = {BEVK_TMA_CONFIGS(X)};
 #undef X
 static const int kNumTmaConfigs = (int)(sizeof kTmaConfigs / sizeof kTmaConfigs[0]);
@@ -161,11 +162,12 @@ struct bevk_ctx {
   int tma_stage_bytes = 0;
   long long tma_items = 0, tma_box_bytes = 0, tma_entries = 0, tma_gather_entries = 0;
   std::vector<int2> tma_shapes;
-  DevBuf d_ttiles, d_titems, d_tlut;
+  DevBuf d_ttiles, d_titems, d_tlut, d_unit_counter;
   struct MapSet { const void* base = nullptr; long long stride = 0, frames = 0; DevBuf d; unsigned long long used = 0; };
   MapSet maps[4];
   unsigned long long map_clock = 0;
   int tma_cfg = 0;                          // index into kTmaConfigs
+  int tma_backoff_ns = 0;                   // BEVK_TMA_BACKOFF (read at finalize): producer poll interval when the ring is full
   int tma_grid[8][4] = {};                  // [config] resident CTAs of k_bev_tma<BAL, NB>: index = 2*BAL + {NB=1:0, 4:1}
   DevBuf d_stack_ptrs;                      // pointer table of a frame stack (BALANCE pre-passes read frames through a table)
   const void* stack_ptrs_base = nullptr; long long stack_ptrs_stride = 0, stack_ptrs_n = 0;
@@ -181,6 +183,9 @@ struct bevk_ctx {
     DevBuf d_slabs;
     long long last_link_bytes = 0;
   } shard;
+  // nvJPEG ingest (bevk_jpeg_decode): library handle + decoder state, created on first use
+  void* jpeg_handle = nullptr; void* jpeg_state = nullptr;
+  DevBuf d_jpeg_frames, d_jpeg_canvas;
   // CUDA graphs captured from the device-pointer entry points (bevk_graph_*)
   bool capturing = false;
   long long capture_launches0 = 0;
@@ -230,6 +235,7 @@ int bevk_ctx_create(int device, bevk_ctx** out) {
 }
 
 static void shard_release(bevk_ctx* c);
+static void jpeg_release(bevk_ctx* c);
 
 int bevk_ctx_destroy(bevk_ctx* c) {
   if (!c) return BEVK_OK;
@@ -238,10 +244,11 @@ int bevk_ctx_destroy(bevk_ctx* c) {
   for (DevBuf* b : {&c->s_src, &c->s_dst, &c->s_m1, &c->s_m2, &c->s_o1, &c->s_o2, &c->d_tiles, &c->d_items, &c->d_lut,
                     &c->d_hsv, &c->d_frames, &c->d_ptrs, &c->d_canvas, &c->d_car, &c->d_vsum, &c->d_delta, &c->d_csum,
                     &c->d_spans, &c->d_bal, &c->d_bal_ptrs, &c->d_user_ptrs, &c->d_ttiles, &c->d_titems, &c->d_tlut,
-                    &c->d_stack_ptrs})
+                    &c->d_stack_ptrs, &c->d_jpeg_frames, &c->d_jpeg_canvas, &c->d_unit_counter})
     b->release();
   for (auto& m : c->maps) m.d.release();
   shard_release(c);
+  jpeg_release(c);
   for (auto& g : c->graphs) { if (g.x) cudaGraphExecDestroy(g.x); if (g.g) cudaGraphDestroy(g.g); }
   for (auto& u : c->und) { u.map1.release(); u.map2.release(); }
   for (auto& k : c->cam) { k.map1.release(); k.map2.release(); }
@@ -603,10 +610,10 @@ int bevk_blend_masks(bevk_ctx* c, const uint8_t* polys, const int32_t* lines, in
 struct TmaFns { const void* fn[4]; };
 static TmaFns tma_fns(int cfg) {
   int i = 0;
-#define X(FS, ST, MC)                                                                                            \
-  if (i++ == cfg)                                                                                                \
-    return TmaFns{{(const void*)k_bev_tma<false, 1, FS, ST, MC>, (const void*)k_bev_tma<false, 4, FS, ST, MC>,     \
-                   (const void*)k_bev_tma<true, 1, FS, ST, MC>, (const void*)k_bev_tma<true, 4, FS, ST, MC>}};
+#define X(FS, ST, MC, EG)                                                                                              \
+  if (i++ == cfg)                                                                                                      \
+    return TmaFns{{(const void*)k_bev_tma<false, 1, FS, ST, MC, EG>, (const void*)k_bev_tma<false, 4, FS, ST, MC, EG>,   \
+                   (const void*)k_bev_tma<true, 1, FS, ST, MC, EG>, (const void*)k_bev_tma<true, 4, FS, ST, MC, EG>}};
   BEVK_TMA_CONFIGS(X)
 #undef X
   return TmaFns{{nullptr, nullptr, nullptr, nullptr}};
@@ -683,12 +690,14 @@ int bevk_bev_finalize(bevk_ctx* c) {
   c->tma_planned = false;
   c->tma_cfg = 0;
   if (const char* env = getenv("BEVK_TMA_CFG")) {
-    int fs = 0, st = 0;
-    if (sscanf(env, "%d,%d", &fs, &st) == 2)
+    int fs = 0, st = 0, eg = 0;
+    if (sscanf(env, "%d,%d,%d", &fs, &st, &eg) == 3)
       for (int i = 0; i < kNumTmaConfigs; ++i)
-        if (kTmaConfigs[i].fs == fs && kTmaConfigs[i].stages == st) c->tma_cfg = i;
+        if (kTmaConfigs[i].fs == fs && kTmaConfigs[i].stages == st && kTmaConfigs[i].eg == eg) c->tma_cfg = i;
   }
   c->tma_stage_bytes = kTmaConfigs[c->tma_cfg].fs;
+  c->tma_backoff_ns = 0;
+  if (const char* env = getenv("BEVK_TMA_BACKOFF")) c->tma_backoff_ns = std::max(0, atoi(env));
   {
     TmaPlan tp;
     std::vector<const short*> p1(NC);
@@ -698,7 +707,8 @@ int bevk_bev_finalize(bevk_ctx* c) {
     const char* env = getenv("BEVK_TMA");
     const bool want = !(env && atoi(env) == 0) && ((unsigned)FW * 3u) % 16u == 0;
     if (want) {
-      build_tma_plan(NC, FW, FH, BW, BH, c->bev_interp == BEVK_INTER_NEAREST, p1.data(), p2.data(), pm.data(), c->tma_stage_bytes, true, tp);
+      build_tma_plan(NC, FW, FH, BW, BH, c->bev_interp == BEVK_INTER_NEAREST, p1.data(), p2.data(), pm.data(), c->tma_stage_bytes, true, tp,
+                     kTmaConfigs[c->tma_cfg].eg);
       RET(c->d_ttiles.ensure(tp.tiles.size() * sizeof(int4)));
       RET(c->d_titems.ensure(std::max<size_t>(1, tp.items.size()) * sizeof(TmaItem)));
       RET(c->d_tlut.ensure(std::max<size_t>(1, tp.lut.size()) * sizeof(uint4)));
@@ -722,7 +732,7 @@ int bevk_bev_finalize(bevk_ctx* c) {
     const int nb[4] = {1, 4, 1, 4};
     for (int i = 0; i < 4; ++i) {
       int per_sm = 0;
-      const size_t smem = bev_tma_smem_bytes(nb[i], kTmaConfigs[c->tma_cfg].fs, kTmaConfigs[c->tma_cfg].stages);
+      const size_t smem = bev_tma_smem_bytes(nb[i], kTmaConfigs[c->tma_cfg].fs, kTmaConfigs[c->tma_cfg].stages, kTmaConfigs[c->tma_cfg].eg);
       CU(cudaFuncSetAttribute(f.fn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f.fn[i], TMA_THREADS, smem));
       c->tma_grid[c->tma_cfg][i] = std::max(1, per_sm) * prop.multiProcessorCount;
@@ -866,7 +876,7 @@ static int launch_bev_tma(bevk_ctx* c, const TmaParams& P, int nbu, bool bal) {
   const int variant = (bal ? 2 : 0) + (nbu == 4 ? 1 : 0);
   const TmaConfig cfg = kTmaConfigs[c->tma_cfg];
   const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(units, c->tma_grid[c->tma_cfg][variant]));
-  const size_t smem = bev_tma_smem_bytes(nbu, cfg.fs, cfg.stages);
+  const size_t smem = bev_tma_smem_bytes(nbu, cfg.fs, cfg.stages, cfg.eg);
   void* args[] = {const_cast<TmaParams*>(&P)};
   CU(cudaLaunchKernel(tma_fns(c->tma_cfg).fn[variant], dim3(blocks), dim3(TMA_THREADS), args, smem, c->stream));
   LAUNCHED(c);
@@ -948,6 +958,10 @@ static int run_device(bevk_ctx* c, FrameSrc src, int batch, const void* d_car, i
     T.n_tiles = P.n_tiles; T.batch = batch; T.out = P.out; T.BW = P.BW; T.BH = P.BH; T.canvas_bytes = P.canvas_bytes;
     T.car = P.car; T.csum = P.csum; T.cam_lo = cam_lo; T.cam_hi = cam_hi;
     T.out_pitch = P.out_pitch; T.ox = P.ox; T.oy = P.oy; T.ox1 = P.ox1; T.oy1 = P.oy1;
+    T.backoff_ns = c->tma_backoff_ns;
+    RET(c->d_unit_counter.ensure(256));
+    CU(cudaMemsetAsync(c->d_unit_counter.p, 0, 4, c->stream));
+    T.unit_counter = c->d_unit_counter.as<unsigned>();
     RET(launch_bev_tma(c, T, nbu, bal));
     c->last_path = 2;
   } else {
@@ -1466,6 +1480,104 @@ int bevk_bev_run_sharded(bevk_ctx* c, const void* d_frames, int64_t frame_stride
 }
 
 int64_t bevk_shard_last_link_bytes(bevk_ctx* c) { return c ? c->shard.last_link_bytes : 0; }
+
+// ------------------------------------------------------------------ JPEG ingest on the device (nvJPEG, dlopen'ed)
+// The reference reads its frames with cv2.imread (SurroundBirdEyeView/surroundBEV.py:328-332, Tools/undistort.py:65):
+// decode on the host, then -- here -- 3 bytes per pixel over PCIe.  bevk_jpeg_decode ships the compressed stream
+// instead and decodes it straight into the frame stack the BEV / undistort entry points read.
+namespace {
+struct NvjpegImage { unsigned char* channel[4]; size_t pitch[4]; };
+struct Nvjpeg {
+  void* lib = nullptr;
+  int (*CreateSimple)(void**) = nullptr;
+  int (*Destroy)(void*) = nullptr;
+  int (*StateCreate)(void*, void**) = nullptr;
+  int (*StateDestroy)(void*) = nullptr;
+  int (*GetImageInfo)(void*, const unsigned char*, size_t, int*, int*, int*, int*) = nullptr;
+  int (*Decode)(void*, void*, const unsigned char*, size_t, int, NvjpegImage*, cudaStream_t) = nullptr;
+  bool ok = false;
+};
+Nvjpeg& nvjpeg() {
+  static Nvjpeg n;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    for (const char* name : {"libnvjpeg.so.12", "libnvjpeg.so", "/usr/local/cuda/lib64/libnvjpeg.so.12"}) {
+      n.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if (n.lib) break;
+    }
+    if (n.lib) {
+      n.CreateSimple = reinterpret_cast<decltype(n.CreateSimple)>(dlsym(n.lib, "nvjpegCreateSimple"));
+      n.Destroy = reinterpret_cast<decltype(n.Destroy)>(dlsym(n.lib, "nvjpegDestroy"));
+      n.StateCreate = reinterpret_cast<decltype(n.StateCreate)>(dlsym(n.lib, "nvjpegJpegStateCreate"));
+      n.StateDestroy = reinterpret_cast<decltype(n.StateDestroy)>(dlsym(n.lib, "nvjpegJpegStateDestroy"));
+      n.GetImageInfo = reinterpret_cast<decltype(n.GetImageInfo)>(dlsym(n.lib, "nvjpegGetImageInfo"));
+      n.Decode = reinterpret_cast<decltype(n.Decode)>(dlsym(n.lib, "nvjpegDecode"));
+      n.ok = n.CreateSimple && n.Destroy && n.StateCreate && n.StateDestroy && n.GetImageInfo && n.Decode;
+    }
+  }
+  return n;
+}
+const int kNvjpegOutputBGRI = 6;   // NVJPEG_OUTPUT_BGRI: interleaved BGR in channel[0], what cv2.imread's layout is
+}  // namespace
+
+static void jpeg_release(bevk_ctx* c) {
+  if (c->jpeg_state && nvjpeg().ok) nvjpeg().StateDestroy(c->jpeg_state);
+  if (c->jpeg_handle && nvjpeg().ok) nvjpeg().Destroy(c->jpeg_handle);
+  c->jpeg_state = c->jpeg_handle = nullptr;
+}
+
+int bevk_jpeg_decode(bevk_ctx* c, const uint8_t* const* jpegs, const uint64_t* sizes, int n, int width, int height, void* d_frames,
+                     int64_t frame_stride) {
+  NvtxRange nvtx_call("bevk_jpeg_decode (nvJPEG -> frame stack)");
+  RET(use(c));
+  if (!jpegs || !sizes || !d_frames || n < 1) return fail(BEVK_ERR_ARG, "bad argument");
+  if (width <= 0 || height <= 0 || frame_stride < (int64_t)width * height * 3) return fail(BEVK_ERR_ARG, "bad frame geometry / stride");
+  if (!nvjpeg().ok) return fail(BEVK_ERR_UNSUPPORTED, "nvJPEG (libnvjpeg.so.12) could not be loaded");
+  if (!c->jpeg_handle) {
+    int r = nvjpeg().CreateSimple(&c->jpeg_handle);
+    if (r != 0) { c->jpeg_handle = nullptr; return fail(BEVK_ERR_CUDA, "nvjpegCreateSimple failed: %d", r); }
+    r = nvjpeg().StateCreate(c->jpeg_handle, &c->jpeg_state);
+    if (r != 0) { jpeg_release(c); return fail(BEVK_ERR_CUDA, "nvjpegJpegStateCreate failed: %d", r); }
+  }
+  for (int i = 0; i < n; ++i) {
+    if (!jpegs[i] || !sizes[i]) return fail(BEVK_ERR_ARG, "JPEG stream %d is empty", i);
+    int comps = 0, sub = 0, w[4] = {0, 0, 0, 0}, h[4] = {0, 0, 0, 0};
+    int r = nvjpeg().GetImageInfo(c->jpeg_handle, jpegs[i], (size_t)sizes[i], &comps, &sub, w, h);
+    if (r != 0) return fail(BEVK_ERR_ARG, "stream %d is not a JPEG nvJPEG can parse (status %d)", i, r);
+    if (w[0] != width || h[0] != height) return fail(BEVK_ERR_ARG, "stream %d is %dx%d, the frame stack holds %dx%d", i, w[0], h[0], width, height);
+    NvjpegImage dst{};
+    dst.channel[0] = reinterpret_cast<unsigned char*>(d_frames) + (size_t)i * frame_stride;
+    dst.pitch[0] = (size_t)width * 3;
+    r = nvjpeg().Decode(c->jpeg_handle, c->jpeg_state, jpegs[i], (size_t)sizes[i], kNvjpegOutputBGRI, &dst, c->stream);
+    if (r != 0) return fail(BEVK_ERR_CUDA, "nvjpegDecode(stream %d) failed: %d", i, r);
+  }
+  return BEVK_OK;
+}
+
+// BevGenerator.__call__ on JPEG streams: decode the batch into the library's frame stack, render, read the canvases back.
+int bevk_bev_run_jpeg(bevk_ctx* c, const uint8_t* const* jpegs, const uint64_t* sizes, int batch, const uint8_t* car, int flags,
+                      uint8_t* out) {
+  NvtxRange nvtx_call("bevk_bev_run_jpeg (JPEG streams -> host canvases)");
+  RET(use(c));
+  if (!c->planned) return fail(BEVK_ERR_ARG, "bevk_bev_finalize not called");
+  if (!jpegs || !sizes || !out || batch < 1) return fail(BEVK_ERR_ARG, "bad argument");
+  const size_t fbytes = (size_t)c->FW * c->FH * 3, fpad = (fbytes + 255) & ~size_t(255), cbytes = (size_t)c->BW * c->BH * 3;
+  const int nf = batch * c->n_cam;
+  RET(c->d_jpeg_frames.ensure(fpad * nf));
+  RET(c->d_jpeg_canvas.ensure(cbytes * batch));
+  RET(bevk_jpeg_decode(c, jpegs, sizes, nf, c->FW, c->FH, c->d_jpeg_frames.p, (int64_t)fpad));
+  if (car) {
+    RET(c->d_car.ensure(cbytes));
+    CU(cudaMemcpyAsync(c->d_car.p, car, cbytes, cudaMemcpyHostToDevice, c->stream));
+  }
+  c->timed = false;
+  RET(run_device(c, stack_src(c->d_jpeg_frames.p, (long long)fpad), batch, car ? c->d_car.p : nullptr, flags, c->d_jpeg_canvas.p, 0,
+                 BEVK_MAX_CAMERAS));
+  CU(cudaMemcpyAsync(out, c->d_jpeg_canvas.p, cbytes * batch, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BEVK_OK;
+}
 
 // ------------------------------------------------------------------ CUDA graphs
 // Stream capture of whatever the device-pointer entry points enqueue between begin and end; replayed with one call.

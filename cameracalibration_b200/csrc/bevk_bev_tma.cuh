@@ -10,9 +10,12 @@
 //     frame-sets of the unit with ONE cp.async.bulk.tensor.3d (SASS UTMALDG) into a ring of shared-memory stages,
 //     completion on an mbarrier.  Taps outside the frame need no special path: TMA zero-fills out-of-bounds words,
 //     which is exactly cv2.remap's BORDER_CONSTANT 0.
-//   * the eight consumer warps read their taps from shared memory (LDS with immediate offsets for frame-set and
-//     word; ~1.6 bank wavefronts per load instead of 4.4 L1 tag look-ups per global load, profiles/), and release
-//     the stage through a second mbarrier;
+//   * the producer also copies the item's LUT entries (cp.async.bulk, SASS UBLKCP) and writes a 32-byte descriptor of
+//     the work (what to do with the slot, where the tile is, whether a write-out follows) into the same ring slot, so the
+//     eight consumer warps never touch global memory on their way: they wait for a slot, read the descriptor, the
+//     entries (LDS.128) and their taps (LDS with immediate offsets for frame-set and word; ~1.4 bank wavefronts per
+//     load instead of 4.4 L1 tag look-ups per global load, profiles/) from shared memory, and release the slot through
+//     a second mbarrier.  Every latency of the global side is the producer's, which runs STAGES slots ahead;
 //   * a stage holds 4 FS bytes: the boxes of four frame-sets of FS bytes each, or -- for the heavily minified near
 //     field, where 256 samples need 12-24 KB of source -- two boxes of 2 FS or one of 4 FS; such items take 2 or 4
 //     PASSES over their entries, one ring slot per pass.  Only what does not even fit 4 FS (discontinuities of the
@@ -64,6 +67,8 @@ struct TmaParams {
   // output window (camera-sharded runs render only the tile-aligned bounding box of their cameras' masks, a "slab"):
   // canvas pixels [ox,ox1) x [oy,oy1) go to out + (y-oy)*out_pitch + (x-ox)*3; the full canvas is 0,0,BW,BH, pitch 3*BW
   int out_pitch, ox, oy, ox1, oy1;
+  int backoff_ns;                // producer poll interval while the ring is full (0: spin)
+  unsigned* unit_counter;        // zeroed before the launch: next unit to hand out
 };
 
 // The six words of one entry -> three sums whose byte 2 is the interpolated channel.
@@ -117,28 +122,43 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  // the suspend-time hint lets the hardware park the warp instead of re-issuing the poll (profiles/r02_d: 9 polls per
+  // wait and 5 % of all issue slots without it)
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "W_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra D_%=;\n\t"
       "bra W_%=;\n\t"
-      "D_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+      "D_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(20000u) : "memory");
 }
 // producer-side wait: one thread per CTA polls; back off between polls so that it does not take issue slots from the
 // eight consumer warps of its own and the neighbouring CTAs (profiles/r02_b: 3.4 M polls per launch without it)
-__device__ __forceinline__ void mbar_wait_backoff(unsigned bar, unsigned parity) {
+__device__ __forceinline__ void mbar_wait_backoff(unsigned bar, unsigned parity, int ns) {
+  if (ns <= 0) { mbar_wait(bar, parity); return; }
   unsigned done = 0;
   while (true) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) break;
-    __nanosleep(200);
+    __nanosleep(ns);
   }
 }
 __device__ __forceinline__ void tma_load_3d(unsigned dst, const void* map, int x, int y, int z, unsigned bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(unsigned addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(unsigned addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ unsigned lds32(unsigned addr) {
   unsigned v;
@@ -155,9 +175,15 @@ __device__ __forceinline__ unsigned lds32_if(unsigned addr, unsigned pred) {
 __device__ __forceinline__ void sts32(unsigned addr, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory"); }
 
-constexpr size_t bev_tma_smem_bytes(int nb, int fs, int stages) {
-  return (size_t)stages * 4 * fs + (size_t)nb * ACC_WORDS * 4 + (size_t)stages * 16 + 1024;   // + alignment slack
+// ring slot: boxes (4 FS) | LUT entries of up to EG groups (EG * 4 KB) | descriptor (128 B reserved)
+__host__ __device__ constexpr int slot_bytes(int fs, int eg) { return 4 * fs + eg * 4096 + 128; }   // a multiple of 128: TMA destinations
+constexpr size_t bev_tma_smem_bytes(int nb, int fs, int stages, int eg) {
+  return (size_t)stages * slot_bytes(fs, eg) + (size_t)nb * ACC_WORDS * 4 + (size_t)stages * 16 + 1024;   // + alignment slack
 }
+
+// slot descriptor, word 0
+constexpr unsigned D_END = 1u, D_GATHER = 2u, D_FIRST = 4u, D_FULL = 8u, D_NOSAT = 16u, D_ORIENT = 32u, D_SYNC = 64u, D_LAST = 128u,
+                   D_NONE = 256u;   // bits 16..19: groups in the slot, 20..22: frame-sets of the pass, 24..26: first frame-set of the pass
 
 // GATHER items (boxes that do not fit a stage): one entry applied to the NB frame-sets of the unit, taps from global
 // memory as in the round-1 kernel.  `aa`: shared address of the entry's accumulator word of frame-set 0.
@@ -201,20 +227,17 @@ __device__ __forceinline__ void gather_entry(const TmaParams& P, const uint4 e, 
   }
 }
 
-// TMA items: the groups [k0,k1) of one LUT block applied to NBP staged boxes (one pass).  RS: stage bytes between the
-// boxes of consecutive frame-sets.  FIRST: this camera stores (zeros where its mask is 0), later cameras add; FULL: every
-// weight of the item is 255.
-template <int NBP, int RS, bool FIRST, bool FULL>
-__device__ __forceinline__ void tma_item(const uint4* __restrict__ L, int k0, int k1, unsigned sbase, unsigned aa, unsigned astep,
-                                         bool nosat) {
-  L += k0 * 256;
-  aa += k0 * astep;
-  uint4 nxt = __ldg(L);
+// TMA slots: `nk` groups of LUT entries (in the slot, `ent` = this thread's first entry) applied to NBP staged boxes.
+// RS: slot bytes between the boxes of consecutive frame-sets.  FIRST: this camera stores (zeros where its mask is 0),
+// later cameras add; FULL: every weight of the item is 255.
+template <int NBP, int RS, bool FIRST, bool FULL, bool HALVES, bool NOSAT>
+__device__ __forceinline__ void tma_item(unsigned ent, int nk, unsigned sbase, unsigned aa, unsigned astep) {
+  uint4 nxt = lds128(ent);
 #pragma unroll 1
-  for (int k = k0; k < k1; ++k, aa += astep) {
+  for (int k = 0; k < nk; ++k, aa += astep) {
     const uint4 e = nxt;
-    L += 256;
-    if (k + 1 < k1) nxt = __ldg(L);
+    ent += 4096;
+    if (k + 1 < nk) nxt = lds128(ent);
     if (!(e.w & T_ACTIVE)) {
       if (FIRST) {
 #pragma unroll
@@ -224,9 +247,8 @@ __device__ __forceinline__ void tma_item(const uint4* __restrict__ L, int k0, in
     }
     const unsigned o0 = sbase + (e.x & 0xffffu), o1 = sbase + (e.x >> 16);
     const unsigned sh8 = (e.w >> 14) & 24u, wm = e.w & 0x1ffffu, third = sh8 == 24u;
-    // two frame-sets at a time: 12 words in flight cover the shared-memory latency, and the register budget allows three
-    // CTAs per SM (24 words in flight cost an occupancy step for nothing)
-    constexpr int G = NBP < 2 ? 1 : 2;
+    // HALVES (3 CTAs per SM configurations): two frame-sets at a time, 12 words in flight, to stay inside 72 registers
+    constexpr int G = HALVES && NBP > 2 ? 2 : NBP;
 #pragma unroll
     for (int h = 0; h < NBP; h += G) {
       unsigned a0[G], a1[G], a2[G], b0[G], b1[G], b2[G];
@@ -243,7 +265,7 @@ __device__ __forceinline__ void tma_item(const uint4* __restrict__ L, int k0, in
         unsigned v = weight_pack<FULL>(sb, sg, sr, wm);
         if (!FIRST) {
           const unsigned old = lds32(aa + (h + j) * ACC_WORDS * 4);
-          v = nosat ? v + old : sat_add_bgr(v, old);                      // cv2.add chain, reference camera order
+          v = NOSAT ? v + old : sat_add_bgr(v, old);                      // cv2.add chain, reference camera order
         }
         sts32(aa + (h + j) * ACC_WORDS * 4, v);
       }
@@ -251,23 +273,28 @@ __device__ __forceinline__ void tma_item(const uint4* __restrict__ L, int k0, in
   }
 }
 
-// one pass of a TMA item: NBP frame-sets whose boxes lie RS bytes apart in the stage
-template <int NBP, int RS>
-__device__ __forceinline__ void tma_pass(const uint4* __restrict__ L, int k0, int k1, unsigned sbase, unsigned aa, unsigned astep,
-                                         bool first, bool full, bool nosat) {
-  if (!first) tma_item<NBP, RS, false, false>(L, k0, k1, sbase, aa, astep, nosat);
-  else if (NBP == 4 && full) tma_item<NBP, RS, true, true>(L, k0, k1, sbase, aa, astep, nosat);
-  else tma_item<NBP, RS, true, false>(L, k0, k1, sbase, aa, astep, nosat);
+// one pass of a TMA item: NBP frame-sets whose boxes lie RS bytes apart in the slot
+template <int NBP, int RS, bool HALVES>
+__device__ __forceinline__ void tma_pass(unsigned ent, int nk, unsigned sbase, unsigned aa, unsigned astep, bool first, bool full,
+                                         bool nosat) {
+  if (!first) {   // NOSAT: the masks of the tile sum to <= 255 everywhere (always so for the reference's blend masks): plain add
+    if (nosat) tma_item<NBP, RS, false, false, HALVES, true>(ent, nk, sbase, aa, astep);
+    else tma_item<NBP, RS, false, false, HALVES, false>(ent, nk, sbase, aa, astep);
+  } else if (NBP == 4 && full) tma_item<NBP, RS, true, true, HALVES, true>(ent, nk, sbase, aa, astep);
+  else tma_item<NBP, RS, true, false, HALVES, true>(ent, nk, sbase, aa, astep);
 }
 
-template <bool BAL, int NB, int FS, int STAGES, int MINCTAS>
+// EG: LUT-entry groups a ring slot can hold (the plan's items never have more)
+template <bool BAL, int NB, int FS, int STAGES, int MINCTAS, int EG>
 __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParams P) {
-  constexpr int SB = 4 * FS;   // bytes of one ring slot
+  constexpr int SB = 4 * FS;                      // box bytes of one ring slot
+  constexpr int SLOT = slot_bytes(FS, EG);        // boxes | entries | descriptor
+  constexpr int ENT_OFF = SB, DESC_OFF = SB + EG * 4096;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // stages need 128-byte alignment for cp.async.bulk.tensor; align the base to 1024 (pointer arithmetic only, so the
+  // slots need 128-byte alignment for cp.async.bulk.tensor; align the base to 1024 (pointer arithmetic only, so the
   // compiler keeps the shared address space)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned* acc = reinterpret_cast<unsigned*>(smem + (size_t)STAGES * SB);   // [NB][ACC_WORDS] packed BGRX
+  unsigned* acc = reinterpret_cast<unsigned*>(smem + (size_t)STAGES * SLOT);   // [NB][ACC_WORDS] packed BGRX
   const unsigned bar_full = smem_u32(acc + NB * ACC_WORDS), bar_empty = bar_full + 8 * STAGES;
   const unsigned stage0 = smem_u32(smem), acc_u32 = smem_u32(acc);
   __shared__ unsigned long long s_sum[BAL ? 3 * NB : 1];
@@ -275,7 +302,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
   if (BAL && t < 3 * NB) s_sum[t] = 0ull;
   if (t == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 1);                      // the producer's arrive.expect_tx
+      mbar_init(bar_full + 8 * s, 1);                      // the producer's arrive(.expect_tx)
       mbar_init(bar_empty + 8 * s, TMA_CONSUMERS / 32);    // one arrival per consumer warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -285,90 +312,126 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
   const long long n_units = (long long)P.n_tiles * groups;
 
   if (t >= TMA_CONSUMERS) {
-    // ---------------- producer: one thread walks the same (unit, item, pass) sequence and keeps the ring full
+    // ---------------- producer: one thread turns the plan into ring slots and stays STAGES slots ahead of the consumers
     if (t == TMA_CONSUMERS) {
       unsigned n = 0;
-      for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        const int tile_id = (int)(unit % P.n_tiles);
-        const int b0 = (int)(unit / P.n_tiles) * NB;
+      auto post = [&](uint4 d0, unsigned cam, unsigned tx, const void* ent_src, unsigned ent_bytes, const uint8_t* map, int np,
+                      int rs, int bx, int by, int z0) {
+        const unsigned s = n % STAGES, ph = (n / STAGES) & 1u;
+        const unsigned slot = stage0 + s * SLOT, full = bar_full + 8 * s;
+        mbar_wait_backoff(bar_empty + 8 * s, ph ^ 1u, P.backoff_ns);   // consumers have left this slot
+        sts128(slot + DESC_OFF, d0);
+        sts32(slot + DESC_OFF + 16, cam);
+        if (tx) mbar_expect_tx(full, tx); else mbar_arrive(full);
+        if (ent_bytes) bulk_copy(slot + ENT_OFF, ent_src, ent_bytes, full);
+        for (int j = 0; j < np; ++j) tma_load_3d(slot + j * rs, map, bx, by, z0 + j * P.n_cam, full);
+        ++n;
+      };
+      const bool filtered = P.cam_lo > 0 || P.cam_hi < 8;   // BEVK_MAX_CAMERAS
+      // Units are handed out dynamically (one atomic per unit, only this thread needs it: the consumers follow the ring):
+      // unit u = tile u / groups of the cost-sorted tile list, frame-set group u % groups -- heavy tiles first, so the
+      // CTAs finish together.  The next unit's id and tile record are fetched while the current unit is being posted.
+      long long unit = (long long)atomicAdd(P.unit_counter, 1u);
+      int4 tile = unit < n_units ? __ldg(P.tiles + (int)(unit / groups)) : make_int4(0, 0, 0, 0);
+      while (unit < n_units) {
+        const long long next_unit = (long long)atomicAdd(P.unit_counter, 1u);
+        const int4 next_tile = next_unit < n_units ? __ldg(P.tiles + (int)(next_unit / groups)) : make_int4(0, 0, 0, 0);
+        const int b0 = (int)(unit % groups) * NB;
         const int nb = min(NB, P.batch - b0);
-        const int4 tile = __ldg(P.tiles + tile_id);
-        for (int it = tile.z; it < tile.z + tile.w; ++it) {
-          const int4 i0 = __ldg(reinterpret_cast<const int4*>(P.items + it));
-          const int4 i1 = __ldg(reinterpret_cast<const int4*>(P.items + it) + 1);
-          const int cam = (short)(i0.y & 0xffff), flags = (i0.y >> 24) & 0xff;
-          if (cam < P.cam_lo || cam >= P.cam_hi || (flags & ITEM_GATHER)) continue;
-          const uint8_t* map = P.maps + (size_t)((unsigned)i0.z >> 16) * TMA_DESC_BYTES;
-          const int rs = i1.z, fpp = min(NB, SB / rs);     // frame-sets per pass
-          for (int p = 0; p < nb; p += fpp) {
-            const unsigned s = n % STAGES, ph = (n / STAGES) & 1u;
-            const int np = min(fpp, nb - p);
-            mbar_wait_backoff(bar_empty + 8 * s, ph ^ 1u); // consumers have left this slot
-            mbar_expect_tx(bar_full + 8 * s, (unsigned)np * (unsigned)i1.y);
-            for (int j = 0; j < np; ++j)
-              tma_load_3d(stage0 + s * SB + j * rs, map, i0.w, i1.x, (b0 + p + j) * P.n_cam + cam, bar_full + 8 * s);
-            ++n;
+        const unsigned dz = (unsigned)tile.x | ((unsigned)tile.y << 16), dw = (unsigned)b0 | ((unsigned)nb << 16);
+        // last item of this unit that belongs to a camera of the call
+        int last_it = tile.z + tile.w - 1;
+        if (filtered)
+          for (; last_it >= tile.z; --last_it) {
+            const int cam = (short)(__ldg(reinterpret_cast<const int*>(P.items + last_it) + 1) & 0xffff);
+            if (cam >= P.cam_lo && cam < P.cam_hi) break;
+          }
+        if (last_it < tile.z) {   // no camera of the call touches the tile (car hole, or another rank's cameras): zeros
+          post(make_uint4(D_SYNC | D_LAST | D_NONE, 0u, dz, dw), 0u, 0u, nullptr, 0u, nullptr, 0, 0, 0, 0, 0);
+        } else {
+          int first_cam = -1, prev_orient = -1;
+          int4 n0 = __ldg(reinterpret_cast<const int4*>(P.items + tile.z));
+          int4 n1 = __ldg(reinterpret_cast<const int4*>(P.items + tile.z) + 1);
+          for (int it = tile.z; it <= last_it; ++it) {
+            const int4 i0 = n0, i1 = n1;
+            if (it < last_it) {   // the next item's record travels while this one is posted
+              n0 = __ldg(reinterpret_cast<const int4*>(P.items + it + 1));
+              n1 = __ldg(reinterpret_cast<const int4*>(P.items + it + 1) + 1);
+            }
+            const int cam = (short)(i0.y & 0xffff), orient = (i0.y >> 16) & 0xff, iflags = (i0.y >> 24) & 0xff;
+            if (cam < P.cam_lo || cam >= P.cam_hi) continue;
+            const int k0 = i0.z & 0xff, nk = ((i0.z >> 8) & 0xff) - k0;
+            unsigned f = 0;
+            if (first_cam < 0) { first_cam = cam; f |= D_SYNC; }               // the previous unit's write-out has read the accumulators
+            if (cam == first_cam) f |= D_FIRST;                                // this camera stores, later ones add (cv2.add order)
+            if (prev_orient >= 0 && prev_orient != orient) f |= D_SYNC;         // accumulator ownership changes with the orientation
+            prev_orient = orient;
+            if (orient) f |= D_ORIENT;
+            if (iflags & ITEM_NOSAT) f |= D_NOSAT;
+            if (iflags & ITEM_FULL) f |= D_FULL;
+            f |= (unsigned)nk << 16 | (unsigned)k0 << 28;
+            const uint4* ent_src = P.lut + (size_t)i0.x * (TILE * TILE) + k0 * 256;
+            const unsigned ent_bytes = (unsigned)nk * 4096u;
+            if (iflags & ITEM_GATHER) {
+              post(make_uint4(f | D_GATHER | (it == last_it ? D_LAST : 0u) | ((unsigned)nb << 20), 0u, dz, dw), (unsigned)cam, ent_bytes,
+                   ent_src, ent_bytes, nullptr, 0, 0, 0, 0, 0);
+              continue;
+            }
+            const uint8_t* map = P.maps + (size_t)((unsigned)i0.z >> 16) * TMA_DESC_BYTES;
+            const int rs = i1.z, fpp = min(NB, SB / rs);                       // frame-sets per pass
+            for (int p = 0; p < nb; p += fpp) {
+              const int np = min(fpp, nb - p);
+              const unsigned fl = f | ((unsigned)np << 20) | ((unsigned)p << 24) | ((it == last_it && p + fpp >= nb) ? D_LAST : 0u);
+              post(make_uint4(p == 0 ? fl : (fl & ~D_SYNC), (unsigned)rs, dz, dw), (unsigned)cam, ent_bytes + (unsigned)np * (unsigned)i1.y,
+                   ent_src, ent_bytes, map, np, rs, i0.w, i1.x, (b0 + p) * P.n_cam + cam);
+            }
           }
         }
+        unit = next_unit; tile = next_tile;
       }
+      post(make_uint4(D_END, 0u, 0u, 0u), 0u, 0u, nullptr, 0u, nullptr, 0, 0, 0, 0, 0);
     }
     return;
   }
 
-  // ---------------- consumers
-  unsigned n = 0;
+  // ---------------- consumers: follow the ring; nothing below reads global memory except GATHER taps and the car overlay
   const int posx = wrp * ACC_WPITCH + lane, stepx = 8 * ACC_WPITCH;   // lanes along canvas x: line k*8+wrp is a row
   const int posy = lane * ACC_WPITCH + wrp, stepy = 8;                // lanes along canvas y: line k*8+wrp is a column
-  for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-    const int tile_id = (int)(unit % P.n_tiles);
-    const int b0 = (int)(unit / P.n_tiles) * NB;
-    const int nb = min(NB, P.batch - b0);
-    const int4 tile = __ldg(P.tiles + tile_id);
-    consumer_sync();   // previous unit's write-out has read the accumulators
-    int first_cam = -1, prev_orient = -1;
-    for (int it = tile.z; it < tile.z + tile.w; ++it) {
-      const int4 i0 = __ldg(reinterpret_cast<const int4*>(P.items + it));
-      const int cam = (short)(i0.y & 0xffff), orient = (i0.y >> 16) & 0xff, flags = (i0.y >> 24) & 0xff;
-      if (cam < P.cam_lo || cam >= P.cam_hi) continue;
-      if (first_cam < 0) first_cam = cam;
-      const bool first = cam == first_cam;               // this camera stores, later ones add (cv2.add order)
-      if (prev_orient >= 0 && prev_orient != orient) consumer_sync();   // accumulator ownership changes with the orientation
-      prev_orient = orient;
-      const int k0 = i0.z & 0xff, k1 = (i0.z >> 8) & 0xff;
-      const bool nosat = (flags & ITEM_NOSAT) != 0;
-      const uint4* __restrict__ L = P.lut + (size_t)i0.x * (TILE * TILE) + t;
-      // shared address of this thread's accumulator word of group 0 / step to the next group, frame-set 0
-      const unsigned aa = acc_u32 + 4u * (unsigned)(orient ? posy : posx), astep = 4u * (unsigned)(orient ? stepy : stepx);
-      if (flags & ITEM_GATHER) {
-        // frame-set j of this unit and camera: frame0 + j * set_stride
+  for (unsigned n = 0;; ++n) {
+    const unsigned s = n % STAGES, ph = (n / STAGES) & 1u;
+    const unsigned slot = stage0 + s * SLOT;
+    mbar_wait(bar_full + 8 * s, ph);                     // descriptor, entries and boxes of this slot have landed
+    const uint4 d = lds128(slot + DESC_OFF);
+    const unsigned flags = d.x;
+    if (flags & D_END) break;
+    const int nk = (flags >> 16) & 15, p = (flags >> 24) & 7, k0 = (flags >> 28) & 3;
+    const bool first = (flags & D_FIRST) != 0, nosat = (flags & D_NOSAT) != 0;
+    const int4 tile = make_int4((int)(d.z & 0xffffu), (int)(d.z >> 16), 0, 0);
+    const int b0 = (int)(d.w & 0xffffu), nb = (int)(d.w >> 16);
+    if (flags & D_SYNC) consumer_sync();
+    if (nk) {
+      const bool orient = (flags & D_ORIENT) != 0;
+      const unsigned astep = 4u * (unsigned)(orient ? stepy : stepx);
+      const unsigned aa = acc_u32 + 4u * (unsigned)(orient ? posy : posx) + (unsigned)k0 * astep + (unsigned)p * (ACC_WORDS * 4);
+      const unsigned ent = slot + ENT_OFF + (unsigned)t * 16u;
+      if (flags & D_GATHER) {
+        const int cam = (int)lds32(slot + DESC_OFF + 16);
         const uint8_t* frame0 = P.base + (long long)(b0 * P.n_cam + cam) * P.frame_stride;
         const long long set_stride = (long long)P.n_cam * P.frame_stride;
-        uint4 nxt = __ldg(L + k0 * 256);
 #pragma unroll 1
-        for (int k = k0; k < k1; ++k) {
-          const uint4 e = nxt;
-          if (k + 1 < k1) nxt = __ldg(L + (k + 1) * 256);
-          gather_entry<NB>(P, e, aa + k * astep, first, nosat, frame0, set_stride, nb);
-        }
+        for (int k = 0; k < nk; ++k) gather_entry<NB>(P, lds128(ent + k * 4096), aa + k * astep, first, nosat, frame0, set_stride, nb);
       } else {
-        const int rs = __ldg(reinterpret_cast<const int*>(P.items + it) + 6);   // TmaItem::fs_bytes
-        const int fpp = min(NB, SB / rs);
-        const bool full = (flags & ITEM_FULL) != 0;
-        for (int p = 0; p < nb; p += fpp) {
-          const unsigned s = n % STAGES, ph = (n / STAGES) & 1u;
-          const unsigned sbase = stage0 + s * SB;
-          mbar_wait(bar_full + 8 * s, ph);               // the boxes of this pass have landed
-          const unsigned ap = aa + (unsigned)p * (ACC_WORDS * 4);
-          if (NB == 4 && fpp == 4) tma_pass<(NB == 4 ? 4 : 1), FS>(L, k0, k1, sbase, ap, astep, first, full, nosat);
-          else if (NB == 4 && fpp == 2) tma_pass<(NB == 4 ? 2 : 1), 2 * FS>(L, k0, k1, sbase, ap, astep, first, full, nosat);
-          else tma_pass<1, 0>(L, k0, k1, sbase, ap, astep, first, full, nosat);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_empty + 8 * s); // this warp no longer reads the slot
-          ++n;
-        }
+        const unsigned rs = d.y;
+        const bool full = (flags & D_FULL) != 0;
+        if (NB == 4 && rs == FS) tma_pass<(NB == 4 ? 4 : 1), FS, (MINCTAS > 2)>(ent, nk, slot, aa, astep, first, full, nosat);
+        else if (NB == 4 && rs == 2 * FS) tma_pass<(NB == 4 ? 2 : 1), 2 * FS, false>(ent, nk, slot, aa, astep, first, full, nosat);
+        else tma_pass<1, 0, false>(ent, nk, slot, aa, astep, first, full, nosat);
       }
     }
-    const bool none = first_cam < 0;                      // tile without a camera (car hole): zeros
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty + 8 * s);       // this warp no longer reads the slot
+    if (!(flags & D_LAST)) continue;
+    const bool none = (flags & D_NONE) != 0;              // tile without a camera (car hole): zeros
     consumer_sync();
     // ---- write the tile(s)
     if (tile.x >= P.ox1 || tile.x + TILE <= P.ox || tile.y >= P.oy1 || tile.y + TILE <= P.oy) continue;   // outside the output window

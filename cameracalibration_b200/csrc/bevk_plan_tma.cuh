@@ -65,7 +65,7 @@ inline int lds_wavefronts(const unsigned* word, int n) {
 
 inline void build_tma_plan(int NC, int FW, int FH, int BW, int BH, bool nearest, const short* const* m1,
                            const unsigned short* const* m2, const uint8_t* const* masks, int stage_bytes, bool allow_tma,
-                           TmaPlan& out) {
+                           TmaPlan& out, int max_groups = 4) {
   const unsigned pitch = (unsigned)FW * 3u;
   const long long frame_bytes = (long long)pitch * FH;
   const int tx = (BW + TILE - 1) / TILE, ty = (BH + TILE - 1) / TILE;
@@ -129,7 +129,9 @@ inline void build_tma_plan(int NC, int FW, int FH, int BW, int BH, bool nearest,
           }
         // recursive partition of the groups [g0,g1)
         struct Range { int g0, g1; };
-        std::vector<Range> todo{{0, 4}};
+        std::vector<Range> todo;   // a ring slot holds the entries of at most max_groups groups
+        for (int g = 4 - std::max(1, std::min(4, max_groups)); g >= 0; g -= std::max(1, std::min(4, max_groups)))
+          todo.push_back({g, g + std::max(1, std::min(4, max_groups))});
         std::vector<TmaItem> made;
         while (!todo.empty()) {
           const Range r = todo.back();

@@ -72,6 +72,23 @@ def _cuda_ptr(arr, shape):
     return int(ptr), got
 
 
+def jpeg_decode(jpegs, width: int, height: int, out=None, ctx: L.Context | None = None):
+    """Decode JPEG byte strings on the GPU (nvJPEG) into a uint8 CUDA frame stack [n][height][width][3] (BGR, what
+    cv2.imread's layout is).  ``out``: a CUDA array of that shape; default a new torch tensor.  Enqueued on the ctx
+    stream; returns ``out``."""
+    ctx = ctx or L.default_context()
+    n = len(jpegs)
+    if out is None:
+        import torch
+        out = torch.empty((n, height, width, 3), dtype=torch.uint8, device=torch.device("cuda", ctx.device))
+    d_out = _cuda_ptr(out, (n, height, width, 3))[0]
+    keep = [(C.c_char * len(x)).from_buffer_copy(bytes(x)) for x in jpegs]
+    ptrs = (C.c_void_p * n)(*[C.addressof(k) for k in keep])
+    sizes = (C.c_uint64 * n)(*[len(x) for x in jpegs])
+    L.check(ctx.lib.bevk_jpeg_decode(ctx.h, ptrs, sizes, n, int(width), int(height), C.c_void_p(d_out), width * height * 3))
+    return out
+
+
 def remap(src: np.ndarray, map1: np.ndarray, map2: np.ndarray | None, interpolation: int = INTER_LINEAR,
           ctx: L.Context | None = None, out: np.ndarray | None = None) -> np.ndarray:
     """cv2.remap with CV_16SC2 (+CV_16UC1) maps, BORDER_CONSTANT 0."""
@@ -304,7 +321,12 @@ class BevEngine:
                         raise L.BevkError("all frames of a call must share one row stride")
                 keep.append(img)
                 ptrs[b * self.n_cam + k] = img.ctypes.data
-        out = _out((batch, self.BH, self.BW, 3), out)
+        if out is None:   # a fresh array per call, as the reference returns -- page-locked and recycled (PinnedPool)
+            if getattr(self, "_pool", None) is None:
+                self._pool = L.PinnedPool()
+            out = self._pool.get((batch, self.BH, self.BW, 3))
+        else:
+            out = _out((batch, self.BH, self.BW, 3), out)
         carp = None
         if car is not None:
             car = np.ascontiguousarray(car, np.uint8)
@@ -313,6 +335,38 @@ class BevEngine:
             carp = L.vptr(car)
         L.check(self.ctx.lib.bevk_bev_run(self.ctx.h, ptrs, stride, batch, carp, L.FLAG_BALANCE if balance else 0,
                                           L.vptr(out)))
+        return out
+
+    def run_jpeg(self, jpeg_sets, car: np.ndarray | None = None, balance: bool = False, out: np.ndarray | None = None):
+        """jpeg_sets: list (batch) of lists (n_cam) of JPEG byte strings (the files cv2.imread would open).  The streams
+        are decoded on the GPU (nvJPEG) straight into the frame stack the fused kernel reads: only compressed bytes cross
+        PCIe on the way in.  Pixels are nvJPEG's decode (not libjpeg-turbo's); the BEV path on them is bit-exact."""
+        if not self.finalized:
+            self.finalize()
+        batch = len(jpeg_sets)
+        if batch < 1:
+            raise L.BevkError("run_jpeg() needs at least one frame-set")
+        flat = []
+        for b, fs in enumerate(jpeg_sets):
+            if len(fs) != self.n_cam:
+                raise L.BevkError(f"frame-set {b} has {len(fs)} streams, expected {self.n_cam}")
+            flat += [bytes(x) if not isinstance(x, (bytes, bytearray)) else x for x in fs]
+        keep = [(C.c_char * len(x)).from_buffer_copy(x) if isinstance(x, bytes) else (C.c_char * len(x)).from_buffer(x) for x in flat]
+        ptrs = (C.c_void_p * len(flat))(*[C.addressof(k) for k in keep])
+        sizes = (C.c_uint64 * len(flat))(*[len(x) for x in flat])
+        if out is None:
+            if getattr(self, "_pool", None) is None:
+                self._pool = L.PinnedPool()
+            out = self._pool.get((batch, self.BH, self.BW, 3))
+        else:
+            out = _out((batch, self.BH, self.BW, 3), out)
+        carp = None
+        if car is not None:
+            car = np.ascontiguousarray(car, np.uint8)
+            if car.shape != (self.BH, self.BW, 3):
+                raise L.BevkError("car must be uint8[bev_h][bev_w][3]")
+            carp = L.vptr(car)
+        L.check(self.ctx.lib.bevk_bev_run_jpeg(self.ctx.h, ptrs, sizes, batch, carp, L.FLAG_BALANCE if balance else 0, L.vptr(out)))
         return out
 
     def host_copy_bytes(self, balance: bool = False):

@@ -214,6 +214,21 @@ int64_t bevk_shard_last_link_bytes(bevk_ctx *ctx);
 int bevk_shard_render(bevk_ctx *ctx, const void *d_frames, int64_t frame_stride, int batch, int as_rank, void *d_slabs);
 int bevk_shard_compose(bevk_ctx *ctx, const void *d_slabs, int batch, const void *d_car, void *d_out);
 
+/* ---- JPEG ingest on the device ------------------------------------------------------------------------------
+ * Replaces cv2.imread in front of the path (surroundBEV.py:328-332, Tools/undistort.py:65): n baseline JPEG streams
+ * (host memory) are decoded by nvJPEG (dlopen'ed on first use) into frames 0..n-1 of a device frame stack, BGR
+ * interleaved, row pitch width*3 -- the layout bevk_bev_run_stack and the undistort entry points read.  Only the
+ * compressed bytes cross PCIe.  Every stream must decode to width x height.  The pixels are nvJPEG's, which differ from
+ * libjpeg-turbo's (cv2) by the decoders' IDCT / upsampling rounding; everything downstream is bit-exact on them.
+ * The Huffman stage runs on the calling thread; GPU work is enqueued on the ctx stream. */
+int bevk_jpeg_decode(bevk_ctx *ctx, const uint8_t *const *jpegs, const uint64_t *sizes, int n, int width, int height,
+                     void *d_frames, int64_t frame_stride);
+
+/* BevGenerator.__call__ (surroundBEV.py:312-325) on JPEG streams: jpegs[batch*n_cam] in frame-set-major order as in
+ * bevk_bev_run; decoded on the device, rendered, canvases copied to `out` (host).  Synchronises. */
+int bevk_bev_run_jpeg(bevk_ctx *ctx, const uint8_t *const *jpegs, const uint64_t *sizes, int batch, const uint8_t *car, int flags,
+                      uint8_t *out);
+
 /* ---- CUDA graphs over the device-pointer entry points ------------------------------------------------
  * Everything the "_device" / "_stack" / "_frames" entry points enqueue on the ctx stream between begin and end is
  * captured (stream capture) instead of executed, instantiated once, and replayed `times` times by one call --

@@ -216,7 +216,7 @@ static int mode_balance() {
 // BALANCE sequence (V sums, offsets, balanced row spans, gather, channel sums, gains, car), without threads.
 // in.bin : int32 NC FW FH BW BH nearest balance has_car; per camera map1 int16[BH*BW*2], map2 uint16[BH*BW],
 //          mask u8[BH*BW]; NC frames u8[FH*FW*3]; car u8[BH*BW*3] if has_car.   out.bin: canvas u8[BH*BW*3]
-static int mode_bev(const char* in_path, const char* out_path, int tma_stage_bytes /* 0: round-1 gather plan */) {
+static int mode_bev(const char* in_path, const char* out_path, int tma_stage_bytes /* 0: round-1 gather plan */, int max_groups = 4) {
   FILE* f = fopen(in_path, "rb");
   if (!f) return 5;
   int hd[8];
@@ -281,7 +281,7 @@ static int mode_bev(const char* in_path, const char* out_path, int tma_stage_byt
       std::vector<const unsigned short*> p2(NC);
       std::vector<const uint8_t*> pm(NC);
       for (int k = 0; k < NC; ++k) { p1[k] = m1[k].data(); p2[k] = m2[k].data(); pm[k] = mk[k].data(); }
-      build_tma_plan(NC, FW, FH, BW, BH, nearest != 0, p1.data(), p2.data(), pm.data(), tma_stage_bytes, true, tp);
+      build_tma_plan(NC, FW, FH, BW, BH, nearest != 0, p1.data(), p2.data(), pm.data(), tma_stage_bytes, true, tp, max_groups);
     }
     std::vector<uint8_t> stage((size_t)4 * tma_stage_bytes + 16, 0xEE);   // one ring slot = 4 FS
     for (const int4& tile : tp.tiles) {
@@ -300,6 +300,7 @@ static int mode_bev(const char* in_path, const char* out_path, int tma_stage_byt
           CHECK(item.fs_bytes == tma_stage_bytes || ((item.fs_bytes == 2 * tma_stage_bytes || item.fs_bytes == 4 * tma_stage_bytes) &&
                                                      item.k1 - item.k0 == 1), "frame-set slot size");
           CHECK((item.xw & 3) == 0 && (shape.x & 3) == 0, "box alignment");
+          CHECK(item.k1 - item.k0 <= max_groups, "item exceeds the slot's entry groups");
           model_tma_box(src, FW, FH, shape, item.xw, item.y, stage.data());
         }
         for (int k = item.k0; k < item.k1; ++k)
@@ -465,7 +466,10 @@ int main(int argc, char** argv) {
   if (argc == 9 && !strcmp(argv[1], "gather"))
     return mode_gather(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argv[7], argv[8]);
   if (argc == 4 && !strcmp(argv[1], "bev")) return mode_bev(argv[2], argv[3], 0);
-  if (argc == 5 && !strcmp(argv[1], "bevtma")) { const int r = mode_bev(argv[2], argv[3], atoi(argv[4])); return r ? r : (fails ? 1 : 0); }
+  if ((argc == 5 || argc == 6) && !strcmp(argv[1], "bevtma")) {
+    const int r = mode_bev(argv[2], argv[3], atoi(argv[4]), argc == 6 ? atoi(argv[5]) : 4);
+    return r ? r : (fails ? 1 : 0);
+  }
   if (argc == 2 && !strcmp(argv[1], "balance")) return mode_balance();
   if (argc == 6 && !strcmp(argv[1], "blend")) return mode_blend(atoi(argv[2]), atoi(argv[3]), argv[4], argv[5]);
   if (argc == 7 && !strcmp(argv[1], "bevmaps")) return mode_bevmaps(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argv[6]);
