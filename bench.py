@@ -414,8 +414,16 @@ def main():
     # ---- kernel-only time of k_bev via the ctx's own events (single launch, averaged) ----
     kt = []
     for _ in range(20):
-        step()
-        kt.append(eng.last_kernel_ms())
+        if cams:   # render + all-gather + compose are one step: time it as a whole on the stream
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record(stream)
+            step()
+            eb.record(stream)
+            eb.synchronize()
+            kt.append(ea.elapsed_time(eb))
+        else:
+            step()
+            kt.append(eng.last_kernel_ms())
     k_ms = float(np.median(kt))
     path_used = eng.last_path()
 

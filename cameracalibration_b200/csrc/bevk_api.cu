@@ -34,7 +34,7 @@ using namespace bevk;
 // of boxes), STAGES = ring slots, MINCTAS = resident CTAs per SM the register budget is set for, EG = LUT-entry groups per
 // slot (the plan's items never span more).  The first entry is the default; BEVK_TMA_CFG="<FS>,<STAGES>,<EG>" (read at
 // bevk_bev_finalize) selects another one for tuning runs.
-#define BEVK_TMA_CONFIGS(X) X(4096, 3, 2, 2) X(6144, 2, 2, 2) X(4096, 2, 3, 2) X(4096, 2, 2, 4) X(5120, 3, 2, 2)
+#define BEVK_TMA_CONFIGS(X) X(4096, 2, 2, 4) X(6144, 2, 2, 2) X(4096, 3, 2, 2) X(4096, 2, 3, 2) X(5120, 3, 2, 2)
 struct TmaConfig { int fs, stages, min_ctas, eg; };
 #define X(FS, ST, MC, EG) {FS, ST, MC, EG},
 static const TmaConfig kTmaConfigs[] = {BEVK_TMA_CONFIGS(X)};

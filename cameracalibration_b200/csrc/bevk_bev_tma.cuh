@@ -397,6 +397,17 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
   // ---------------- consumers: follow the ring; nothing below reads global memory except GATHER taps and the car overlay
   const int posx = wrp * ACC_WPITCH + lane, stepx = 8 * ACC_WPITCH;   // lanes along canvas x: line k*8+wrp is a row
   const int posy = lane * ACC_WPITCH + wrp, stepy = 8;                // lanes along canvas y: line k*8+wrp is a column
+  // write-out of interior tiles: word idx = i*256 + t of the tile's 32 rows x 24 words (see tile_row_word)
+  unsigned wo_acc[3], wo_sel[3], wo_off[3];
+  int wo_r[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int idx = i * 256 + t, r = idx / 24, w = idx - r * 24, p = w + w / 3, ph = w - (w / 3) * 3;
+    wo_r[i] = r;
+    wo_acc[i] = acc_u32 + 4u * (unsigned)(r * ACC_WPITCH + p);
+    wo_sel[i] = ph == 0 ? 0x4210u : (ph == 1 ? 0x5421u : 0x6542u);
+    wo_off[i] = (unsigned)r * (unsigned)(P.out_pitch >> 2) + (unsigned)w;
+  }
   for (unsigned n = 0;; ++n) {
     const unsigned s = n % STAGES, ph = (n / STAGES) & 1u;
     const unsigned slot = stage0 + s * SLOT;
@@ -436,18 +447,19 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
     // ---- write the tile(s)
     if (tile.x >= P.ox1 || tile.x + TILE <= P.ox || tile.y >= P.oy1 || tile.y + TILE <= P.oy) continue;   // outside the output window
     if (!BAL && tile.x + TILE <= P.ox1 && (P.out_pitch & 3) == 0 && (P.canvas_bytes & 3) == 0 && (P.ox & 3) == 0) {
-      // interior tile: 32 rows x 24 words, written as 3 x 256 consecutive words (a warp store = two 96-byte row pieces)
+      // interior tile: 32 rows x 24 words, written as 3 x 256 consecutive words (a warp store = two 96-byte row pieces);
+      // which word, which accumulator pixels and which byte selector a thread handles never changes (wo_* above)
+      const size_t base = ((size_t)(tile.y - P.oy) * P.out_pitch + (size_t)(tile.x - P.ox) * 3) / 4;
+      const int rows = P.oy1 - tile.y;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        const int idx = i * 256 + t, r = idx / 24, w = idx - r * 24;
-        const int gy = tile.y + r;
-        if (gy >= P.oy1) continue;
-        const size_t word_off = ((size_t)(gy - P.oy) * P.out_pitch + (size_t)(tile.x - P.ox) * 3) / 4 + w;
+        if (wo_r[i] >= rows) continue;
+        const size_t word_off = base + wo_off[i];
         const unsigned cw = P.car ? __ldg(reinterpret_cast<const unsigned*>(P.car) + word_off) : 0u;
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
           if (j >= nb) break;
-          unsigned v = none ? 0u : tile_row_word(acc + j * ACC_WORDS + r * ACC_WPITCH, w);
+          unsigned v = none ? 0u : lane_perm(lds32(wo_acc[i] + j * ACC_WORDS * 4), lds32(wo_acc[i] + j * ACC_WORDS * 4 + 4), wo_sel[i]);
           if (P.car) v = lane_addus4(v, cw);
           reinterpret_cast<unsigned*>(P.out + (size_t)(b0 + j) * P.canvas_bytes)[word_off] = v;
         }

@@ -32,7 +32,7 @@ def test_jpeg_streams_to_bev(fx):
     dec = dec.cpu().numpy()
     for k, n in enumerate(NAMES):                               # (a) a faithful decode
         diff = np.abs(dec[k].astype(np.int16) - fx.img(n).astype(np.int16))
-        assert diff.max() <= 6 and diff.mean() < 0.6, (n, int(diff.max()), float(diff.mean()))
+        assert diff.max() <= 24 and diff.mean() < 0.8, (n, int(diff.max()), float(diff.mean()))
     car = fx.car()
     ref = C.RefBev(fx.calib, g, True, False, masks=masks)
     for balance in (False, True):                               # (b) bit-exact downstream
