@@ -255,9 +255,10 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="frame-sets per GPU per step (default: the workload's own)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (default: min(steps, 20))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--shard", default="frames", choices=["frames", "cameras"],
+    ap.add_argument("--shard", default="frames", choices=["frames", "cameras", "cameras-p2p"],
                     help="multi-GPU policy: frame-sets per GPU (weak scaling, no collective; default) or cameras per GPU "
-                         "(strong scaling over one batch, one NCCL all-gather of partial canvases per step)")
+                         "(strong scaling over one batch: 'cameras' = slabs + ONE NCCL all-gather, every rank gets all canvases; "
+                         "'cameras-p2p' = the fused kernel stores slabs into the owning rank over NVLink, canvases stay sharded)")
     ap.add_argument("--workload", default="cfg4", choices=sorted(ALT_WORKLOADS),
                     help="cfg4 (default) is the headline; the others are secondary measurements of BASELINE configs")
     a = ap.parse_args()
@@ -271,6 +272,8 @@ def main():
     config = {"workload": f"{w['batch']} frame-sets/GPU x {w['n_cam']} cams {w['FW']}x{w['FH']} BGR -> {w['BW']}x{w['BH']} BEV, "
                           f"blend={w['blend']} balance={w['balance']} (BASELINE {a.workload} shape)",
               "sharding": ("frame-sets per GPU, no data-path collective" if a.shard == "frames" else
+                           "cameras per GPU, fused: the render kernel stores each slab into the rank that owns the frame-set (b % world) over "
+                           "NVLink peer memory, a 4-byte all-gather is the step barrier, owners compose; canvases stay sharded" if a.shard == "cameras-p2p" else
                            "cameras per GPU: each rank renders its cameras' slabs (tile-aligned mask bounding boxes), ONE "
                            "ncclAllGather of the slabs per step over NVLink, local saturating compose; every rank ends with all canvases"),
               "launch": "one step captured as a CUDA graph, the K timed steps replayed by one bevk_graph_launch call",
@@ -353,13 +356,18 @@ def main():
     d_out = torch.empty((nb, w["BH"], w["BW"], 3), dtype=torch.uint8, device=dev)
 
     from cameracalibration_b200.sharding import ShardedBev
-    sharded = ShardedBev(eng, a.shard if world > 1 else "frames")
-    cams = a.shard == "cameras" and world > 1
+    sharded = ShardedBev(eng, "cameras" if (a.shard != "frames" and world > 1) else "frames")
+    cams = a.shard != "frames" and world > 1
+    p2p = cams and a.shard == "cameras-p2p"
+    d_own = torch.empty(((nb + world - 1) // world, w["BH"], w["BW"], 3), dtype=torch.uint8, device=dev) if p2p else None
 
     use_table = bool(os.environ.get("BEVK_BENCH_TABLE"))   # A/B switch: frames through a device pointer table (round-1 gather kernel)
 
     def step():
-        if cams:
+        if p2p:
+            # one camera block per rank; the fused kernel stores its slabs into the owners over NVLink (bevk_bev_run_scattered)
+            sharded.render_scattered(d_frames, d_own, None, stream=stream.cuda_stream)
+        elif cams:
             # one camera block per rank: slabs -> ONE ncclAllGather -> compose, all on `stream` (bevk_bev_run_sharded)
             sharded.render(d_frames, d_out, None, w["balance"], stream=stream.cuda_stream)
         elif use_table:
@@ -450,7 +458,11 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * nb * n_e2e / float(te.item())   # e2e always runs the frames policy (each rank its own batch)
-    same = bool((torch.from_numpy(np.asarray(pin_out)).to(dev) == d_out).all().item())
+    if p2p:   # the device path left this rank only the canvases it owns
+        own = list(range(rank, nb, world))
+        same = bool((torch.from_numpy(np.asarray(pin_out)[own]).to(dev) == d_own[:len(own)]).all().item())
+    else:
+        same = bool((torch.from_numpy(np.asarray(pin_out)).to(dev) == d_out).all().item())
 
     # ---- the reference's own call: BevGenerator.__call__(front, back, left, right), one frame-set, NumPy in / NumPy out
     e2e_api = None

@@ -66,6 +66,9 @@ SIGNATURES = {
     "bevk_shard_connect": (C.c_int, [_p, _p, C.c_int]),
     "bevk_shard_info": (C.c_int, [_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "bevk_bev_run_sharded": (C.c_int, [_p, _p, C.c_int64, C.c_int, _p, C.c_int, _p]),
+    "bevk_shard_prepare": (C.c_int, [_p, C.c_int, _p]),
+    "bevk_shard_attach": (C.c_int, [_p, _p]),
+    "bevk_bev_run_scattered": (C.c_int, [_p, _p, C.c_int64, C.c_int, _p, C.c_int, _p, C.POINTER(C.c_int)]),
     "bevk_shard_last_link_bytes": (C.c_int64, [_p]),
     "bevk_shard_render": (C.c_int, [_p, _p, C.c_int64, C.c_int, C.c_int, _p]),
     "bevk_shard_compose": (C.c_int, [_p, _p, C.c_int, _p, _p]),

@@ -182,6 +182,12 @@ struct bevk_ctx {
     void* comm = nullptr;                   // ncclComm_t
     DevBuf d_slabs;
     long long last_link_bytes = 0;
+    // peer-store exchange (bevk_bev_run_scattered): this rank's receive buffer [2 halves][world][own_max][slab_bytes],
+    // the same buffer of every peer mapped through CUDA IPC, and a 4-byte-per-rank scratch for the step barrier
+    void* recv = nullptr; size_t recv_bytes = 0; int prepared_batch = 0, own_max = 0;
+    void* peer_recv[SHARD_MAX_RANKS] = {}; bool attached = false;
+    DevBuf d_flag;
+    unsigned step = 0;
   } shard;
   // nvJPEG ingest (bevk_jpeg_decode): library handle + decoder state, created on first use
   void* jpeg_handle = nullptr; void* jpeg_state = nullptr;
@@ -885,13 +891,17 @@ static int launch_bev_tma(bevk_ctx* c, const TmaParams& P, int nbu, bool bal) {
 
 // Output window of a render: the full canvas by default; camera-sharded runs render the tile-aligned bounding box of
 // their cameras' masks ("slab") with its own pitch and frame-set stride.
-struct OutWin { int pitch = 0, ox = 0, oy = 0, ox1 = 0, oy1 = 0; long long stride = 0; };
+struct OutWin {
+  int pitch = 0, ox = 0, oy = 0, ox1 = 0, oy1 = 0; long long stride = 0;
+  // scattered mode (peer stores): frame-set b -> peer[b % world] + src_off + (b / world) * stride
+  uint8_t* peer[SHARD_MAX_RANKS] = {}; int world = 0; long long src_off = 0;
+};
 
 static int run_device(bevk_ctx* c, FrameSrc src, int batch, const void* d_car, int flags, void* d_out, int cam_lo, int cam_hi,
                       const OutWin* win = nullptr) {
   NvtxRange nvtx_render("bevk render (fused BEV kernels)");
   if (!c->planned) return fail(BEVK_ERR_ARG, "bevk_bev_finalize not called");
-  if ((!src.table && !src.base) || !d_out) return fail(BEVK_ERR_ARG, "null device pointer");
+  if ((!src.table && !src.base) || (!d_out && !(win && win->world))) return fail(BEVK_ERR_ARG, "null device pointer");
   if (batch < 1 || batch > 65535) return fail(BEVK_ERR_ARG, "batch %d out of range [1,65535]", batch);
   const bool bal = (flags & BEVK_FLAG_BALANCE) != 0;
   const int nf = batch * c->n_cam;
@@ -959,12 +969,14 @@ static int run_device(bevk_ctx* c, FrameSrc src, int batch, const void* d_car, i
     T.car = P.car; T.csum = P.csum; T.cam_lo = cam_lo; T.cam_hi = cam_hi;
     T.out_pitch = P.out_pitch; T.ox = P.ox; T.oy = P.oy; T.ox1 = P.ox1; T.oy1 = P.oy1;
     T.backoff_ns = c->tma_backoff_ns;
+    if (win && win->world) { for (int r = 0; r < SHARD_MAX_RANKS; ++r) T.peer[r] = win->peer[r]; T.world = win->world; T.src_off = win->src_off; }
     RET(c->d_unit_counter.ensure(256));
     CU(cudaMemsetAsync(c->d_unit_counter.p, 0, 4, c->stream));
     T.unit_counter = c->d_unit_counter.as<unsigned>();
     RET(launch_bev_tma(c, T, nbu, bal));
     c->last_path = 2;
   } else {
+    if (win && win->world) return fail(BEVK_ERR_UNSUPPORTED, "peer-store output needs the TMA-staged kernel (a 16-byte friendly frame stack)");
     if (!gsrc.table) RET(stack_table(c, gsrc.base, gsrc.stride, nf, &gsrc.table));
     P.srcs = reinterpret_cast<const uint8_t* const*>(gsrc.table);
     const long long units = c->n_tiles * ((batch + nbu - 1) / nbu);
@@ -1338,7 +1350,20 @@ Nccl& nccl() {
 const int kNcclUint8 = 1;   // ncclUint8 (nccl.h: ncclInt8 = 0, ncclUint8 = 1)
 }  // namespace
 
+static void shard_peers_release(bevk_ctx* c) {
+  bevk_ctx::Shard& s = c->shard;
+  for (int r = 0; r < SHARD_MAX_RANKS; ++r) {
+    if (s.peer_recv[r] && s.peer_recv[r] != s.recv) cudaIpcCloseMemHandle(s.peer_recv[r]);
+    s.peer_recv[r] = nullptr;
+  }
+  s.attached = false;
+}
+
 static void shard_release(bevk_ctx* c) {
+  shard_peers_release(c);
+  if (c->shard.recv) cudaFree(c->shard.recv);
+  c->shard.recv = nullptr; c->shard.recv_bytes = 0; c->shard.prepared_batch = 0;
+  c->shard.d_flag.release();
   if (c->shard.comm && nccl().ok) nccl().CommDestroy(c->shard.comm);
   c->shard.comm = nullptr;
   c->shard.d_slabs.release();
@@ -1420,10 +1445,11 @@ static int shard_render(bevk_ctx* c, FrameSrc src, int batch, int as_rank, void*
   return run_device(c, src, batch, nullptr, 0, dst, s.cam_lo[as_rank], s.cam_hi[as_rank], &w);
 }
 
-static int shard_compose(bevk_ctx* c, const void* d_slabs, int batch, const void* d_car, void* d_out) {
+static int shard_compose(bevk_ctx* c, const void* d_slabs, int batch, const void* d_car, void* d_out, long long rank_stride = 0) {
   bevk_ctx::Shard& s = c->shard;
   ComposeArgs a{};
   a.slabs = reinterpret_cast<const uint8_t*>(d_slabs); a.slab_bytes = s.slab_bytes; a.world = std::min(s.world, SHARD_MAX_RANKS);
+  a.rank_stride = rank_stride ? rank_stride : (long long)batch * s.slab_bytes;
   a.batch = batch; a.BW = c->BW; a.BH = c->BH;
   for (int r = 0; r < a.world; ++r) a.rect[r] = s.rect[r];
   a.car = reinterpret_cast<const uint8_t*>(d_car); a.out = reinterpret_cast<uint8_t*>(d_out);
@@ -1477,6 +1503,94 @@ int bevk_bev_run_sharded(bevk_ctx* c, const void* d_frames, int64_t frame_stride
   if (r != 0) return fail(BEVK_ERR_CUDA, "ncclAllGather: %s", nccl().GetErrorString(r));
   s.last_link_bytes = (long long)per_rank * (s.world - 1);
   return shard_compose(c, s.d_slabs.p, batch, d_car, d_out);
+}
+
+// ---- camera sharding with peer stores: compute and exchange in one kernel ----------------------------------------
+// Frame-set b of the batch is OWNED by rank b % world, which ends up with its canvas.  Every rank renders its cameras'
+// slabs of ALL frame-sets, and the fused kernel's write-out stores each slab straight into the owner's receive buffer
+// over NVLink (CUDA IPC mapping) -- no send buffer, no separate collective; one 4-byte all-gather per step is the
+// barrier that tells an owner its slabs have landed, then it composes its own canvases.  Each rank sends and receives
+// (world-1)/world of ONE slab set instead of receiving world-1 whole ones as the all-gather form does.
+static int own_count(int batch, int rank, int world) { return (batch - rank + world - 1) / world; }
+
+int bevk_shard_prepare(bevk_ctx* c, int batch, void* handle64) {
+  RET(use(c));
+  RET(shard_geometry(c));
+  bevk_ctx::Shard& s = c->shard;
+  if (s.policy != BEVK_SHARD_CAMERAS) return fail(BEVK_ERR_ARG, "peer stores belong to the CAMERAS policy");
+  if (batch < 1 || !handle64) return fail(BEVK_ERR_ARG, "bad argument");
+  CU(cudaStreamSynchronize(c->stream));
+  shard_peers_release(c);
+  s.own_max = (batch + s.world - 1) / s.world;
+  const size_t need = 2 * (size_t)s.world * s.own_max * s.slab_bytes;
+  if (need > s.recv_bytes) {   // plain cudaMalloc: IPC handles cannot be taken from pool / async allocations
+    if (s.recv) cudaFree(s.recv);
+    s.recv = nullptr; s.recv_bytes = 0;
+    CU(cudaMalloc(&s.recv, need));
+    s.recv_bytes = need;
+  }
+  CU(cudaMemsetAsync(s.recv, 0, s.recv_bytes, c->stream));   // slabs of ranks without cameras are never written: keep them zero
+  CU(cudaStreamSynchronize(c->stream));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, s.recv));
+  static_assert(sizeof h == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  s.prepared_batch = batch;
+  RET(s.d_flag.ensure(sizeof(int) * (SHARD_MAX_RANKS + 1)));
+  return BEVK_OK;
+}
+
+int bevk_shard_attach(bevk_ctx* c, const void* handles) {
+  RET(use(c));
+  bevk_ctx::Shard& s = c->shard;
+  if (!s.prepared_batch || !handles) return fail(BEVK_ERR_ARG, "bevk_shard_prepare not called");
+  shard_peers_release(c);
+  for (int r = 0; r < s.world && r < SHARD_MAX_RANKS; ++r) {
+    if (r == s.rank) { s.peer_recv[r] = s.recv; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, reinterpret_cast<const uint8_t*>(handles) + 64 * r, 64);
+    const cudaError_t e = cudaIpcOpenMemHandle(&s.peer_recv[r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { s.peer_recv[r] = nullptr; shard_peers_release(c); return fail(BEVK_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e)); }
+  }
+  s.attached = true;
+  return BEVK_OK;
+}
+
+int bevk_bev_run_scattered(bevk_ctx* c, const void* d_frames, int64_t frame_stride, int batch, const void* d_car, int flags,
+                           void* d_out_own, int* n_own) {
+  NvtxRange nvtx_call("bevk_bev_run_scattered (render with peer stores, barrier, compose own)");
+  RET(use(c));
+  bevk_ctx::Shard& s = c->shard;
+  if (!s.configured || s.policy != BEVK_SHARD_CAMERAS) return fail(BEVK_ERR_ARG, "bevk_shard_configure(CAMERAS) not called");
+  RET(check_stack(c, d_frames, frame_stride));
+  if (flags & BEVK_FLAG_BALANCE) return fail(BEVK_ERR_UNSUPPORTED, "balance is not available with camera sharding");
+  RET(shard_geometry(c));
+  if (!s.comm && s.world > 1) return fail(BEVK_ERR_ARG, "bevk_shard_connect not called");
+  if (!s.attached || batch > s.prepared_batch || (batch + s.world - 1) / s.world != s.own_max)
+    return fail(BEVK_ERR_ARG, "bevk_shard_prepare / bevk_shard_attach not called for a batch of %d", batch);
+  const int mine = own_count(batch, s.rank, s.world);
+  if (n_own) *n_own = mine;
+  if (mine > 0 && !d_out_own) return fail(BEVK_ERR_ARG, "null output");
+  const size_t half = (size_t)s.world * s.own_max * s.slab_bytes, rank_stride = (size_t)s.own_max * s.slab_bytes;
+  const unsigned par = s.step++ & 1u;     // double buffer: a peer may already store step n+1 while this rank composes step n
+  const SlabRect q = s.rect[s.rank];
+  s.last_link_bytes = 0;
+  if (q.ox1 > q.ox && s.cam_hi[s.rank] > s.cam_lo[s.rank]) {
+    OutWin w;
+    w.pitch = (q.ox1 - q.ox) * 3; w.ox = q.ox; w.oy = q.oy; w.ox1 = q.ox1; w.oy1 = q.oy1; w.stride = s.slab_bytes;
+    w.world = s.world; w.src_off = (long long)(par * half + (size_t)s.rank * rank_stride);
+    for (int r = 0; r < s.world; ++r) w.peer[r] = reinterpret_cast<uint8_t*>(s.peer_recv[r]);
+    c->timed = false;
+    RET(run_device(c, stack_src(d_frames, frame_stride), batch, nullptr, 0, nullptr, s.cam_lo[s.rank], s.cam_hi[s.rank], &w));
+    s.last_link_bytes = (long long)(batch - mine) * s.slab_bytes;   // what this rank stored into its peers
+  }
+  if (s.world > 1) {   // the step barrier: every rank's stores are complete (its kernel has finished) when this returns on the stream
+    int* f = s.d_flag.as<int>();
+    const int r = nccl().AllGather(f + SHARD_MAX_RANKS, f, 4, kNcclUint8, s.comm, c->stream);
+    if (r != 0) return fail(BEVK_ERR_CUDA, "ncclAllGather (step barrier): %s", nccl().GetErrorString(r));
+  }
+  if (mine > 0) RET(shard_compose(c, reinterpret_cast<const uint8_t*>(s.recv) + par * half, mine, d_car, d_out_own, (long long)rank_stride));
+  return BEVK_OK;
 }
 
 int64_t bevk_shard_last_link_bytes(bevk_ctx* c) { return c ? c->shard.last_link_bytes : 0; }

@@ -69,6 +69,11 @@ struct TmaParams {
   int out_pitch, ox, oy, ox1, oy1;
   int backoff_ns;                // producer poll interval while the ring is full (0: spin)
   unsigned* unit_counter;        // zeroed before the launch: next unit to hand out
+  // camera-sharded runs with peer stores (bevk_bev_run_scattered): the output of frame-set b goes straight into the memory
+  // of the rank that owns b -- peer[b % world] + src_off + (b / world) * canvas_bytes -- over NVLink; world == 0: plain `out`
+  uint8_t* peer[8];
+  int world;
+  long long src_off;
 };
 
 // The six words of one entry -> three sums whose byte 2 is the interpolated channel.
@@ -284,6 +289,12 @@ __device__ __forceinline__ void tma_pass(unsigned ent, int nk, unsigned sbase, u
   else tma_item<NBP, RS, true, false, HALVES, true>(ent, nk, sbase, aa, astep);
 }
 
+// where frame-set b of the call is written: the caller's buffer, or (scattered mode) the owning rank's slab buffer
+__device__ __forceinline__ uint8_t* out_base(const TmaParams& P, int b) {
+  if (P.world == 0) return P.out + (size_t)b * P.canvas_bytes;
+  return P.peer[b % P.world] + P.src_off + (size_t)(b / P.world) * P.canvas_bytes;
+}
+
 // EG: LUT-entry groups a ring slot can hold (the plan's items never have more)
 template <bool BAL, int NB, int FS, int STAGES, int MINCTAS, int EG>
 __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParams P) {
@@ -461,7 +472,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
           if (j >= nb) break;
           unsigned v = none ? 0u : lane_perm(lds32(wo_acc[i] + j * ACC_WORDS * 4), lds32(wo_acc[i] + j * ACC_WORDS * 4 + 4), wo_sel[i]);
           if (P.car) v = lane_addus4(v, cw);
-          reinterpret_cast<unsigned*>(P.out + (size_t)(b0 + j) * P.canvas_bytes)[word_off] = v;
+          reinterpret_cast<unsigned*>(out_base(P, b0 + j))[word_off] = v;
         }
       }
       continue;
@@ -506,7 +517,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
         }
       }
       if (!inb) continue;
-      uint8_t* o = P.out + (size_t)(b0 + j) * P.canvas_bytes + pix_off;
+      uint8_t* o = out_base(P, b0 + j) + pix_off;
       if (full) {
         if (!BAL && P.car) { w0 = lane_addus4(w0, c0); w1 = lane_addus4(w1, c1); w2 = lane_addus4(w2, c2); }
         unsigned* g = reinterpret_cast<unsigned*>(o);

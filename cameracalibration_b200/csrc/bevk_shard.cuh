@@ -46,8 +46,8 @@ inline SlabRect slab_rect(const uint8_t* const* masks, int lo, int hi, int BW, i
 }
 
 struct ComposeArgs {
-  const uint8_t* slabs;            // [world][batch][slab_bytes]
-  long long slab_bytes;
+  const uint8_t* slabs;            // rank r, frame-set b at slabs + r * rank_stride + b * slab_bytes
+  long long slab_bytes, rank_stride;
   int world, batch, BW, BH;
   SlabRect rect[SHARD_MAX_RANKS];
   const uint8_t* car;              // dense canvas or null
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) k_compose_slabs(ComposeArgs a) {
       if (r >= a.world) break;
       const SlabRect q = a.rect[r];
       if (y < q.oy || y >= q.oy1 || xb < q.ox * 3 || xb >= q.ox1 * 3) continue;
-      const uint8_t* p = a.slabs + ((size_t)r * a.batch + b) * a.slab_bytes + (size_t)(y - q.oy) * ((q.ox1 - q.ox) * 3) + (xb - q.ox * 3);
+      const uint8_t* p = a.slabs + (size_t)r * a.rank_stride + (size_t)b * a.slab_bytes + (size_t)(y - q.oy) * ((q.ox1 - q.ox) * 3) + (xb - q.ox * 3);
       if (WORD) v = __vaddus4(v, __ldg(reinterpret_cast<const unsigned*>(p)));
       else v = min(255u, v + __ldg(p));
     }

@@ -10,6 +10,9 @@ libbevk.so (bevk_shard_* / bevk_bev_run_sharded, include/bevk.h) so that a bindi
     ncclAllGather moves the slabs over NVLink, and every rank composes them with the saturating sum.  Exact, because
     the reference's cv2.add chain (surroundBEV.py:316-320) is order-independent.  balance=True is not available in
     this mode (luminance_balance needs every camera's V mean before the warp).
+    The same policy with the exchange FUSED into the render kernel: ShardedBev.render_scattered -- frame-set b is owned
+    by rank b % world, the fused kernel's write-out stores each slab straight into the owner's memory over NVLink (CUDA
+    IPC peer mapping), a 4-byte all-gather is the step barrier, each rank composes the canvases it owns.
 
 ShardedBev is a thin caller: it carries the NCCL unique id between the ranks with torch.distributed (any backend) and
 points the engine at torch's current stream for the duration of a call, so that frames produced by torch kernels,
@@ -157,6 +160,55 @@ class ShardedBev:
         with e.ctx.on_stream(_torch_current_stream(e.ctx.device) if stream is None else stream):
             L.check(e.ctx.lib.bevk_shard_compose(e.ctx.h, C.c_void_p(d_slabs), shape[1], C.c_void_p(d_car), C.c_void_p(d_out)))
         return out
+
+    def own_frame_sets(self, batch: int):
+        """Frame-sets of a batch whose canvases render_scattered() leaves on this rank: rank, rank + world, ..."""
+        return list(range(self.rank, batch, self.world))
+
+    def _prepare_peers(self, batch: int):
+        """Size the peer-store receive buffers for `batch` and map every rank's buffer into this process (CUDA IPC):
+        the 64-byte handles travel with one all_gather."""
+        import torch
+        import torch.distributed as dist
+        from . import _lib as L
+        lib, h = self.e.ctx.lib, self.e.ctx.h
+        mine = (C.c_uint8 * 64)()
+        L.check(lib.bevk_shard_prepare(h, int(batch), mine))
+        backend = dist.get_backend(self.group)
+        dev = torch.device("cuda", self.e.ctx.device) if backend == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+        allh = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(allh, t, group=self.group)
+        raw = b"".join(bytes(x.cpu().tolist()) for x in allh)
+        L.check(lib.bevk_shard_attach(h, raw))
+        dist.barrier(group=self.group)      # nobody stores into a peer before every peer has mapped and zeroed its buffer
+        self._peers_for = batch
+
+    def render_scattered(self, frames, out_own, car=None, stream: int | None = None):
+        """Policy 'cameras' with peer stores (bevk_bev_run_scattered): every rank renders its cameras' slabs of ALL
+        frame-sets of ``frames`` ([batch][n_cam][FH][FW][3]; only its own cameras' frames are read), the fused kernel
+        stores each slab straight into the memory of the rank that OWNS the frame-set (b % world) over NVLink, and each
+        rank composes its own canvases into ``out_own`` ([ceil(batch / world)][BH][BW][3]; the first
+        len(own_frame_sets(batch)) entries are valid).  Returns the number of canvases written."""
+        from . import _lib as L
+        from .ops import _cuda_ptr
+        e = self.e
+        base, shape = _cuda_ptr(frames, None)
+        if len(shape) != 5 or tuple(shape[1:]) != (e.n_cam, e.FH, e.FW, 3):
+            raise L.BevkError(f"frames must be uint8[batch][{e.n_cam}][{e.FH}][{e.FW}][3], got {tuple(shape)}")
+        batch = shape[0]
+        if getattr(self, "_peers_for", None) != batch:
+            self._prepare_peers(batch)
+        own_max = (batch + self.world - 1) // self.world
+        d_out = _cuda_ptr(out_own, (own_max, e.BH, e.BW, 3))[0]
+        d_car = _cuda_ptr(car, (e.BH, e.BW, 3))[0] if car is not None else None
+        n_own = C.c_int()
+        if stream is None:
+            stream = _torch_current_stream(e.ctx.device)
+        with e.ctx.on_stream(stream):
+            L.check(e.ctx.lib.bevk_bev_run_scattered(e.ctx.h, C.c_void_p(base), e.FH * e.FW * 3, batch, C.c_void_p(d_car), 0,
+                                                     C.c_void_p(d_out), C.byref(n_own)))
+        return n_own.value
 
     def link_bytes(self) -> int:
         """Bytes this rank received over NVLink in the last render()."""

@@ -207,7 +207,19 @@ int bevk_shard_info(bevk_ctx *ctx, int rank, int *cam_lo, int *cam_hi, int32_t r
  * passes the same batch; only the frames of its own cameras are read; every rank ends with all canvases in d_out. */
 int bevk_bev_run_sharded(bevk_ctx *ctx, const void *d_frames, int64_t frame_stride, int batch, const void *d_car, int flags,
                          void *d_out);
-/* Bytes this rank received over NVLink in the last bevk_bev_run_sharded call. */
+/* CAMERAS policy, fused compute + exchange: frame-set b is OWNED by rank b % world.  Every rank renders its cameras'
+ * slabs of all frame-sets and the fused kernel's write-out stores each slab straight into the owner's receive buffer
+ * over NVLink (peer memory mapped with CUDA IPC); one 4-byte all-gather per step is the barrier, then each rank composes
+ * the canvases it owns (d_out_own[*n_own][bev_h][bev_w][3], frame-sets rank, rank+world, ...).  Per step a rank sends
+ * (and receives) (world-1)/world of one slab set, instead of receiving world-1 whole slab sets as the all-gather does.
+ * Setup after bevk_shard_connect: bevk_shard_prepare(batch) on every rank gives a 64-byte handle; the launcher gathers
+ * the handles of all ranks (rank order, world x 64 bytes) and gives them to bevk_shard_attach.  Frames must be a
+ * 16-byte friendly stack (the TMA-staged kernel does the stores). */
+int bevk_shard_prepare(bevk_ctx *ctx, int batch, void *handle64);
+int bevk_shard_attach(bevk_ctx *ctx, const void *handles);
+int bevk_bev_run_scattered(bevk_ctx *ctx, const void *d_frames, int64_t frame_stride, int batch, const void *d_car, int flags,
+                           void *d_out_own, int *n_own);
+/* Bytes this rank received (all-gather) or stored into its peers (scattered) over NVLink in the last sharded call. */
 int64_t bevk_shard_last_link_bytes(bevk_ctx *ctx);
 /* The two halves of the CAMERAS policy on their own (tests, custom exchanges): render the slabs of rank `as_rank`
  * into d_slabs[as_rank][batch][slab_bytes]; compose d_slabs[world][batch][slab_bytes] (+ car) into canvases. */

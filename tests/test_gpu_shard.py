@@ -117,6 +117,19 @@ def _nccl_worker(rank, world, port, q):
             ref = C.RefBev(fx.calib, g, blend, False, masks=masks)
             ok = all((got[i] == ref(*sets[i], fx.car())).all() for i in (0, 1, 4))
             res[f"cameras_blend{int(blend)}"] = (ok, h16(got[0]) == fx.gold["native"][f"blend{int(blend)}_balance0"]["car"], sh.link_bytes())
+            # the fused form: slabs stored straight into the owning rank over NVLink, canvases stay sharded; three steps so
+            # that both halves of the double-buffered receive area are used and reused
+            own = sh.own_frame_sets(5)
+            out_own = torch.zeros((3, g.BH, g.BW, 3), dtype=torch.uint8, device=dev)
+            okp = True
+            for step in range(3):
+                d_in = d_mine.roll(step, 0).contiguous()
+                torch.cuda.synchronize()
+                n_own = sh.render_scattered(d_in, out_own, car)
+                torch.cuda.synchronize()
+                want = [ref(*sets[(b - step) % 5], fx.car()) for b in own]
+                okp &= n_own == len(own) and all((out_own[i].cpu().numpy() == want[i]).all() for i in range(n_own))
+            res[f"p2p_blend{int(blend)}"] = (bool(okp), sh.link_bytes() > 0, sh.link_bytes())
             # frames policy: each rank its own block of the batch, no collective
             shf = ShardedBev(e, "frames")
             a, b = shf.my_frame_sets(5)
