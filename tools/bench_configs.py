@@ -65,21 +65,21 @@ def bev_config(fx, name, FW, FH, BW, BH, blend, balance, batches=(1, 32)):
     for nb in batches:
         d = torch.from_numpy(np.stack([np.stack(frames)] * nb)).to(dev)
         fb = FW * FH * 3
-        ptrs = torch.tensor([d.data_ptr() + i * fb for i in range(nb * 4)], dtype=torch.int64, device=dev)
         dcar = torch.from_numpy(car).to(dev)
         dout = torch.empty((nb, BH, BW, 3), dtype=torch.uint8, device=dev)
         torch.cuda.synchronize()
         for _ in range(5):
-            eng.run_device(ptrs.data_ptr(), nb, dout.data_ptr(), dcar.data_ptr(), balance)
+            eng.run_stack(d.data_ptr(), fb, nb, dout.data_ptr(), dcar.data_ptr(), balance)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 50
         e0.record(stream)
         for _ in range(reps):
-            eng.run_device(ptrs.data_ptr(), nb, dout.data_ptr(), dcar.data_ptr(), balance)
+            eng.run_stack(d.data_ptr(), fb, nb, dout.data_ptr(), dcar.data_ptr(), balance)
         e1.record(stream)
         torch.cuda.synchronize()
         out[f"gpu_device_us_per_frame_set_batch{nb}"] = e0.elapsed_time(e1) / reps / nb * 1e3
         assert bool((dout[0].cpu().numpy() == want).all())
+        out["fused_kernel"] = eng.last_path()
     eng.ctx.set_stream(None)
     pin = [pinned_empty(f.shape) for f in frames]
     for p, f in zip(pin, frames):

@@ -13,6 +13,10 @@ timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $O/bench_ref
 echo "== cfg3 / cfg2 bench"
 BEVK_BENCH_NO_API=1 timeout 600 python bench.py --workload cfg3 --steps 50 --warmup 5 --no-cpu-baseline > $O/bench_cfg3.json 2> $O/bench_cfg3.err; tail -c 600 $O/bench_cfg3.json
 BEVK_BENCH_NO_API=1 timeout 600 python bench.py --workload cfg2 --steps 50 --warmup 5 --no-cpu-baseline > $O/bench_cfg2.json 2> $O/bench_cfg2.err; tail -c 600 $O/bench_cfg2.json
+echo "== Tools/undistort.py directory throughput"
+timeout 600 python tools/bench_undistort_dir.py > $O/undistort_dir.json 2> $O/undistort_dir.err; cat $O/undistort_dir.json
+echo "== every BASELINE config next to cv2"
+timeout 900 python tools/bench_configs.py > $O/configs.json 2> $O/configs.err; tail -c 600 $O/configs.json
 echo "== ncu launch lists"
 BEVK_BENCH_NO_API=1 BEVK_BENCH_NO_GRAPH=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 12 -c 60 --csv --log-file $O/launches.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $O/b_ncu.log 2>&1
 BEVK_BENCH_NO_API=1 BEVK_BENCH_NO_GRAPH=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 60 --csv --log-file $O/launches_cfg3.csv python bench.py --workload cfg3 --steps 8 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $O/b_ncu_cfg3.log 2>&1
