@@ -9,7 +9,7 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbevk.so")
+LIB_PATH = os.environ.get("BEVK_LIB_PATH") or os.path.join(_HERE, "libbevk.so")   # BEVK_LIB_PATH: A/B builds on the GPU box
 
 INTER_NEAREST, INTER_LINEAR = 0, 1
 MAPS_UNDISTORT, MAPS_BEV = 0, 1

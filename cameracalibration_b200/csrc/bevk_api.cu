@@ -612,17 +612,18 @@ int bevk_blend_masks(bevk_ctx* c, const uint8_t* polys, const int32_t* lines, in
   return BEVK_OK;
 }
 
-// the four instantiations of one k_bev_tma configuration: {BAL=0,NB=1}, {0,4}, {1,1}, {1,4}
-struct TmaFns { const void* fn[4]; };
+// the instantiations of one k_bev_tma configuration: {BAL=0,NB=1}, {0,4}, {1,1}, {1,4}, and the peer-store forms of the first two
+struct TmaFns { const void* fn[6]; };
 static TmaFns tma_fns(int cfg) {
   int i = 0;
 #define X(FS, ST, MC, EG)                                                                                              \
   if (i++ == cfg)                                                                                                      \
     return TmaFns{{(const void*)k_bev_tma<false, 1, FS, ST, MC, EG>, (const void*)k_bev_tma<false, 4, FS, ST, MC, EG>,   \
-                   (const void*)k_bev_tma<true, 1, FS, ST, MC, EG>, (const void*)k_bev_tma<true, 4, FS, ST, MC, EG>}};
+                   (const void*)k_bev_tma<true, 1, FS, ST, MC, EG>, (const void*)k_bev_tma<true, 4, FS, ST, MC, EG>,     \
+                   (const void*)k_bev_tma<false, 1, FS, ST, MC, EG, true>, (const void*)k_bev_tma<false, 4, FS, ST, MC, EG, true>}};
   BEVK_TMA_CONFIGS(X)
 #undef X
-  return TmaFns{{nullptr, nullptr, nullptr, nullptr}};
+  return TmaFns{{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
 }
 
 // Tile-plan compiler: LUT maps + masks -> per-tile item lists and thread-ordered LUT blocks.
@@ -735,13 +736,13 @@ int bevk_bev_finalize(bevk_ctx* c) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, c->device));
     const TmaFns f = tma_fns(c->tma_cfg);
-    const int nb[4] = {1, 4, 1, 4};
-    for (int i = 0; i < 4; ++i) {
+    const int nb[6] = {1, 4, 1, 4, 1, 4};
+    for (int i = 0; i < 6; ++i) {
       int per_sm = 0;
       const size_t smem = bev_tma_smem_bytes(nb[i], kTmaConfigs[c->tma_cfg].fs, kTmaConfigs[c->tma_cfg].stages, kTmaConfigs[c->tma_cfg].eg);
       CU(cudaFuncSetAttribute(f.fn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f.fn[i], TMA_THREADS, smem));
-      c->tma_grid[c->tma_cfg][i] = std::max(1, per_sm) * prop.multiProcessorCount;
+      if (i < 4) c->tma_grid[c->tma_cfg][i] = std::max(1, per_sm) * prop.multiProcessorCount;
     }
   }
   if (c->bev_grid[0] == 0) {   // persistent grid = resident CTAs of each variant
@@ -884,7 +885,8 @@ static int launch_bev_tma(bevk_ctx* c, const TmaParams& P, int nbu, bool bal) {
   const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(units, c->tma_grid[c->tma_cfg][variant]));
   const size_t smem = bev_tma_smem_bytes(nbu, cfg.fs, cfg.stages, cfg.eg);
   void* args[] = {const_cast<TmaParams*>(&P)};
-  CU(cudaLaunchKernel(tma_fns(c->tma_cfg).fn[variant], dim3(blocks), dim3(TMA_THREADS), args, smem, c->stream));
+  const bool scatter = P.world != 0;   // peer-store output: only without BALANCE (run_device checks)
+  CU(cudaLaunchKernel(tma_fns(c->tma_cfg).fn[scatter ? 4 + (nbu == 4 ? 1 : 0) : variant], dim3(blocks), dim3(TMA_THREADS), args, smem, c->stream));
   LAUNCHED(c);
   return BEVK_OK;
 }
@@ -950,7 +952,7 @@ static int run_device(bevk_ctx* c, FrameSrc src, int batch, const void* d_car, i
       LAUNCHED(c);
       c->bal_ptrs_for = c->d_bal.p; c->bal_ptrs_n = nf; c->bal_ptrs_pad = fpad;
     }
-    k_lum_spans<<<dim3(c->FH, nf), 128, 0, c->stream>>>(srcs, c->d_bal_ptrs.as<uint8_t*>(), c->d_spans.as<int2>(), c->n_cam,
+    k_lum_spans<<<dim3((c->FH + LUM_ROWS - 1) / LUM_ROWS, nf), 128, 0, c->stream>>>(srcs, c->d_bal_ptrs.as<uint8_t*>(), c->d_spans.as<int2>(), c->n_cam,
                                                        c->FW, c->FH, c->d_delta.as<int>(), c->d_hsv.as<int>());
     LAUNCHED(c);
     gsrc.table = c->d_bal_ptrs.p; gsrc.base = c->d_bal.as<uint8_t>(); gsrc.stride = (long long)fpad;
@@ -1453,12 +1455,13 @@ static int shard_compose(bevk_ctx* c, const void* d_slabs, int batch, const void
   a.batch = batch; a.BW = c->BW; a.BH = c->BH;
   for (int r = 0; r < a.world; ++r) a.rect[r] = s.rect[r];
   a.car = reinterpret_cast<const uint8_t*>(d_car); a.out = reinterpret_cast<uint8_t*>(d_out);
-  const long long total = (long long)c->BW * c->BH * 3;
   const bool word = (c->BW % 4) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 3) == 0 && (!d_car || (reinterpret_cast<uintptr_t>(d_car) & 3) == 0) &&
                     (reinterpret_cast<uintptr_t>(d_slabs) & 3) == 0;
-  const int blocks = (int)std::max<long long>(1, std::min<long long>(148 * 8 / std::max(1, std::min(batch, 64)) + 1, total / (4 * 256) + 1));
-  if (word) k_compose_slabs<true><<<dim3(blocks, batch), 256, 0, c->stream>>>(a);
-  else k_compose_slabs<false><<<dim3(blocks, batch), 256, 0, c->stream>>>(a);
+  if (batch > 65535 || c->BH > 65535) return fail(BEVK_ERR_UNSUPPORTED, "compose grid too large");
+  const int units = word ? c->BW * 3 / 4 : c->BW * 3;
+  const dim3 grid((units + 255) / 256, c->BH, batch);
+  if (word) k_compose_slabs<true><<<grid, 256, 0, c->stream>>>(a);
+  else k_compose_slabs<false><<<grid, 256, 0, c->stream>>>(a);
   LAUNCHED(c);
   return BEVK_OK;
 }

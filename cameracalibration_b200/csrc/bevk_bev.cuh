@@ -73,10 +73,6 @@ __host__ __device__ __forceinline__ int ldg8(const uint8_t* p) {
   return *p;
 #endif
 }
-#ifndef BEVK_WRITE_COALESCED
-#define BEVK_WRITE_COALESCED 0
-#endif
-
 // Fast path, phase 2: the six words of one entry -> weighted pixel packed B | G<<8 | R<<16.
 __host__ __device__ __forceinline__ unsigned interp_fast(unsigned sh, unsigned wpx, unsigned wpy, unsigned wm, unsigned a0,
                                                          unsigned a1, unsigned a2, unsigned b0, unsigned b1, unsigned b2) {
@@ -227,29 +223,6 @@ __global__ void __launch_bounds__(256, BEVK_MIN_CTAS) k_bev(BevParams P) {
       __syncthreads();
     }
     if (tile.x >= P.ox1 || tile.x + TILE <= P.ox || tile.y >= P.oy1 || tile.y + TILE <= P.oy) continue;   // outside the output window
-#if BEVK_WRITE_COALESCED
-    // Experiment (default off, not yet measured): interior tiles are written as 3 x 256 consecutive 32-bit
-    // words of the tile's 32 rows x 24 words, so one warp store covers 2 canvas rows (about 3 L1 tag look-ups)
-    // instead of 8 lanes x 4 rows at a 12-byte stride (6.5 look-ups, profiles/r01_k_bev_source_summary.txt).
-    if (!BAL && tile.x + TILE <= P.ox1 && P.out_pitch % 4 == 0 && P.canvas_bytes % 4 == 0 && P.ox % 4 == 0) {
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int idx = i * 256 + t, r = idx / 24, w = idx - r * 24;     // word w of tile row r
-        const int gy = tile.y + r;
-        if (gy >= P.oy1) continue;
-        const size_t word_off = ((size_t)(gy - P.oy) * P.out_pitch + (size_t)(tile.x - P.ox) * 3) / 4 + w;
-        const unsigned cw = P.car ? __ldg(reinterpret_cast<const unsigned*>(P.car) + word_off) : 0u;
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-          if (j >= nb) break;
-          unsigned v = first ? 0u : tile_row_word(acc + j * ACC_WORDS + r * ACC_WPITCH, w);
-          if (P.car) v = lane_addus4(v, cw);
-          reinterpret_cast<unsigned*>(P.out + (size_t)(b0 + j) * P.canvas_bytes)[word_off] = v;
-        }
-      }
-      continue;
-    }
-#endif
     // ---- write the tile(s): thread t -> row t/8, 4 pixels (12 bytes) at pixel 4*(t%8) ----
     const int row = t >> 3, chunk = t & 7;
     const int gy = tile.y + row, gx = tile.x + chunk * 4;

@@ -290,13 +290,14 @@ __device__ __forceinline__ void tma_pass(unsigned ent, int nk, unsigned sbase, u
 }
 
 // where frame-set b of the call is written: the caller's buffer, or (scattered mode) the owning rank's slab buffer
+template <bool SCATTER>
 __device__ __forceinline__ uint8_t* out_base(const TmaParams& P, int b) {
-  if (P.world == 0) return P.out + (size_t)b * P.canvas_bytes;
+  if (!SCATTER) return P.out + (size_t)b * P.canvas_bytes;
   return P.peer[b % P.world] + P.src_off + (size_t)(b / P.world) * P.canvas_bytes;
 }
 
 // EG: LUT-entry groups a ring slot can hold (the plan's items never have more)
-template <bool BAL, int NB, int FS, int STAGES, int MINCTAS, int EG>
+template <bool BAL, int NB, int FS, int STAGES, int MINCTAS, int EG, bool SCATTER = false>
 __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParams P) {
   constexpr int SB = 4 * FS;                      // box bytes of one ring slot
   constexpr int SLOT = slot_bytes(FS, EG);        // boxes | entries | descriptor
@@ -357,8 +358,10 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
             const int cam = (short)(__ldg(reinterpret_cast<const int*>(P.items + last_it) + 1) & 0xffff);
             if (cam >= P.cam_lo && cam < P.cam_hi) break;
           }
-        if (last_it < tile.z) {   // no camera of the call touches the tile (car hole, or another rank's cameras): zeros
-          post(make_uint4(D_SYNC | D_LAST | D_NONE, 0u, dz, dw), 0u, 0u, nullptr, 0u, nullptr, 0, 0, 0, 0, 0);
+        if (last_it < tile.z) {   // no camera of the call touches the tile (car hole, or another rank's cameras): zeros --
+          // unless the tile lies outside the output window altogether (camera-sharded slabs): then there is nothing to do
+          if (!(tile.x >= P.ox1 || tile.x + TILE <= P.ox || tile.y >= P.oy1 || tile.y + TILE <= P.oy))
+            post(make_uint4(D_SYNC | D_LAST | D_NONE, 0u, dz, dw), 0u, 0u, nullptr, 0u, nullptr, 0, 0, 0, 0, 0);
         } else {
           int first_cam = -1, prev_orient = -1;
           int4 n0 = __ldg(reinterpret_cast<const int4*>(P.items + tile.z));
@@ -408,17 +411,6 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
   // ---------------- consumers: follow the ring; nothing below reads global memory except GATHER taps and the car overlay
   const int posx = wrp * ACC_WPITCH + lane, stepx = 8 * ACC_WPITCH;   // lanes along canvas x: line k*8+wrp is a row
   const int posy = lane * ACC_WPITCH + wrp, stepy = 8;                // lanes along canvas y: line k*8+wrp is a column
-  // write-out of interior tiles: word idx = i*256 + t of the tile's 32 rows x 24 words (see tile_row_word)
-  unsigned wo_acc[3], wo_sel[3], wo_off[3];
-  int wo_r[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const int idx = i * 256 + t, r = idx / 24, w = idx - r * 24, p = w + w / 3, ph = w - (w / 3) * 3;
-    wo_r[i] = r;
-    wo_acc[i] = acc_u32 + 4u * (unsigned)(r * ACC_WPITCH + p);
-    wo_sel[i] = ph == 0 ? 0x4210u : (ph == 1 ? 0x5421u : 0x6542u);
-    wo_off[i] = (unsigned)r * (unsigned)(P.out_pitch >> 2) + (unsigned)w;
-  }
   for (unsigned n = 0;; ++n) {
     const unsigned s = n % STAGES, ph = (n / STAGES) & 1u;
     const unsigned slot = stage0 + s * SLOT;
@@ -458,21 +450,20 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
     // ---- write the tile(s)
     if (tile.x >= P.ox1 || tile.x + TILE <= P.ox || tile.y >= P.oy1 || tile.y + TILE <= P.oy) continue;   // outside the output window
     if (!BAL && tile.x + TILE <= P.ox1 && (P.out_pitch & 3) == 0 && (P.canvas_bytes & 3) == 0 && (P.ox & 3) == 0) {
-      // interior tile: 32 rows x 24 words, written as 3 x 256 consecutive words (a warp store = two 96-byte row pieces);
-      // which word, which accumulator pixels and which byte selector a thread handles never changes (wo_* above)
-      const size_t base = ((size_t)(tile.y - P.oy) * P.out_pitch + (size_t)(tile.x - P.ox) * 3) / 4;
-      const int rows = P.oy1 - tile.y;
+      // interior tile: 32 rows x 24 words, written as 3 x 256 consecutive words (a warp store = two 96-byte row pieces)
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        if (wo_r[i] >= rows) continue;
-        const size_t word_off = base + wo_off[i];
+        const int idx = i * 256 + t, r = idx / 24, w = idx - r * 24;
+        const int gy = tile.y + r;
+        if (gy >= P.oy1) continue;
+        const size_t word_off = ((size_t)(gy - P.oy) * P.out_pitch + (size_t)(tile.x - P.ox) * 3) / 4 + w;
         const unsigned cw = P.car ? __ldg(reinterpret_cast<const unsigned*>(P.car) + word_off) : 0u;
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
           if (j >= nb) break;
-          unsigned v = none ? 0u : lane_perm(lds32(wo_acc[i] + j * ACC_WORDS * 4), lds32(wo_acc[i] + j * ACC_WORDS * 4 + 4), wo_sel[i]);
+          unsigned v = none ? 0u : tile_row_word(acc + j * ACC_WORDS + r * ACC_WPITCH, w);
           if (P.car) v = lane_addus4(v, cw);
-          reinterpret_cast<unsigned*>(out_base(P, b0 + j))[word_off] = v;
+          reinterpret_cast<unsigned*>(out_base<SCATTER>(P, b0 + j))[word_off] = v;   // SCATTER: straight into the owning rank over NVLink
         }
       }
       continue;
@@ -517,7 +508,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
         }
       }
       if (!inb) continue;
-      uint8_t* o = out_base(P, b0 + j) + pix_off;
+      uint8_t* o = out_base<SCATTER>(P, b0 + j) + pix_off;
       if (full) {
         if (!BAL && P.car) { w0 = lane_addus4(w0, c0); w1 = lane_addus4(w1, c1); w2 = lane_addus4(w2, c2); }
         unsigned* g = reinterpret_cast<unsigned*>(o);

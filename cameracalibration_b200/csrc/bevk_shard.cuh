@@ -55,34 +55,34 @@ struct ComposeArgs {
 };
 
 #ifdef __CUDACC__
-// grid (blocks, batch).  WORD: canvas rows are whole 32-bit words (BW % 4 == 0) and every slab edge falls on a word
-// boundary (tile-aligned x, or the canvas edge) -> 4 bytes per step; otherwise one byte per step.
+// grid (chunks of 256 units per canvas row, canvas rows, frame-sets): no index arithmetic beyond adds.  WORD: canvas rows
+// are whole 32-bit words (BW % 4 == 0) and every slab edge falls on a word boundary (tile-aligned x, or the canvas edge)
+// -> a unit is 4 bytes; otherwise one byte.
 template <bool WORD>
 __global__ void __launch_bounds__(256) k_compose_slabs(ComposeArgs a) {
-  const int b = blockIdx.y;
-  const long long row_bytes = (long long)a.BW * 3, total = row_bytes * a.BH;
-  const long long n = WORD ? total / 4 : total;
-  uint8_t* out = a.out + (size_t)b * total;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long off = WORD ? i * 4 : i;
-    const int y = (int)(off / row_bytes), xb = (int)(off - (long long)y * row_bytes);
-    unsigned v = 0;
+  const int b = blockIdx.z, y = blockIdx.y;
+  const int row_bytes = a.BW * 3;
+  const int xb = (blockIdx.x * 256 + threadIdx.x) * (WORD ? 4 : 1);
+  if (xb >= row_bytes) return;
+  const size_t off = (size_t)y * row_bytes + xb;
+  unsigned v = 0;
 #pragma unroll
-    for (int r = 0; r < SHARD_MAX_RANKS; ++r) {
-      if (r >= a.world) break;
-      const SlabRect q = a.rect[r];
-      if (y < q.oy || y >= q.oy1 || xb < q.ox * 3 || xb >= q.ox1 * 3) continue;
-      const uint8_t* p = a.slabs + (size_t)r * a.rank_stride + (size_t)b * a.slab_bytes + (size_t)(y - q.oy) * ((q.ox1 - q.ox) * 3) + (xb - q.ox * 3);
-      if (WORD) v = __vaddus4(v, __ldg(reinterpret_cast<const unsigned*>(p)));
-      else v = min(255u, v + __ldg(p));
-    }
-    if (a.car) {
-      if (WORD) v = __vaddus4(v, __ldg(reinterpret_cast<const unsigned*>(a.car + off)));
-      else v = min(255u, v + __ldg(a.car + off));
-    }
-    if (WORD) *reinterpret_cast<unsigned*>(out + off) = v;
-    else out[off] = (uint8_t)v;
+  for (int r = 0; r < SHARD_MAX_RANKS; ++r) {
+    if (r >= a.world) break;
+    const SlabRect q = a.rect[r];
+    if (y < q.oy || y >= q.oy1 || xb < q.ox * 3 || xb >= q.ox1 * 3) continue;
+    const uint8_t* p = a.slabs + (size_t)r * a.rank_stride + (size_t)b * a.slab_bytes + (size_t)(y - q.oy) * ((q.ox1 - q.ox) * 3) + (xb - q.ox * 3);
+    // plain loads (not the read-only path): in peer-store mode other GPUs wrote this memory
+    if (WORD) v = __vaddus4(v, *reinterpret_cast<const unsigned*>(p));
+    else v = min(255u, v + *p);
   }
+  if (a.car) {
+    if (WORD) v = __vaddus4(v, __ldg(reinterpret_cast<const unsigned*>(a.car + off)));
+    else v = min(255u, v + __ldg(a.car + off));
+  }
+  uint8_t* out = a.out + (size_t)b * row_bytes * a.BH;
+  if (WORD) *reinterpret_cast<unsigned*>(out + off) = v;
+  else out[off] = (uint8_t)v;
 }
 #endif
 

@@ -554,7 +554,7 @@ int main(int argc, char** argv) {
             lane_perm(a[2], a[3], 0x6542) == want[2], "4-pixel write-out chunk=%d", chunk);
     }
   }
-  // ---- coalesced write-out index map (BEVK_WRITE_COALESCED): 3 x 256 threads cover 32 rows x 24 words exactly once
+  // ---- coalesced write-out index map (k_bev_tma's interior tiles): 3 x 256 threads cover 32 rows x 24 words exactly once
   {
     int seen[TILE][24] = {};
     for (int i = 0; i < 3; ++i)

@@ -17,6 +17,8 @@ echo "== Tools/undistort.py directory throughput"
 timeout 600 python tools/bench_undistort_dir.py > $O/undistort_dir.json 2> $O/undistort_dir.err; cat $O/undistort_dir.json
 echo "== every BASELINE config next to cv2"
 timeout 900 python tools/bench_configs.py > $O/configs.json 2> $O/configs.err; tail -c 600 $O/configs.json
+echo "== camera-sharded step, halves timed on one GPU"
+timeout 300 python tools/gpu/shard_breakdown.py > $O/shard_breakdown.json 2> $O/shard_breakdown.err; cat $O/shard_breakdown.json
 echo "== ncu launch lists"
 BEVK_BENCH_NO_API=1 BEVK_BENCH_NO_GRAPH=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 12 -c 60 --csv --log-file $O/launches.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $O/b_ncu.log 2>&1
 BEVK_BENCH_NO_API=1 BEVK_BENCH_NO_GRAPH=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 60 --csv --log-file $O/launches_cfg3.csv python bench.py --workload cfg3 --steps 8 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $O/b_ncu_cfg3.log 2>&1
