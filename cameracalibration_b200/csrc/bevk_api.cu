@@ -1455,13 +1455,13 @@ static int shard_compose(bevk_ctx* c, const void* d_slabs, int batch, const void
   a.batch = batch; a.BW = c->BW; a.BH = c->BH;
   for (int r = 0; r < a.world; ++r) a.rect[r] = s.rect[r];
   a.car = reinterpret_cast<const uint8_t*>(d_car); a.out = reinterpret_cast<uint8_t*>(d_out);
-  const bool word = (c->BW % 4) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 3) == 0 && (!d_car || (reinterpret_cast<uintptr_t>(d_car) & 3) == 0) &&
-                    (reinterpret_cast<uintptr_t>(d_slabs) & 3) == 0;
-  if (batch > 65535 || c->BH > 65535) return fail(BEVK_ERR_UNSUPPORTED, "compose grid too large");
-  const int units = word ? c->BW * 3 / 4 : c->BW * 3;
-  const dim3 grid((units + 255) / 256, c->BH, batch);
-  if (word) k_compose_slabs<true><<<grid, 256, 0, c->stream>>>(a);
-  else k_compose_slabs<false><<<grid, 256, 0, c->stream>>>(a);
+  const bool wide = (c->BW % 8) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 7) == 0 && (!d_car || (reinterpret_cast<uintptr_t>(d_car) & 7) == 0) &&
+                    (reinterpret_cast<uintptr_t>(d_slabs) & 7) == 0 && (s.slab_bytes & 7) == 0 && (a.rank_stride & 7) == 0;
+  if (batch > 65535 || c->BH > 65535 * COMPOSE_ROWS) return fail(BEVK_ERR_UNSUPPORTED, "compose grid too large");
+  const int units = wide ? c->BW * 3 / 8 : c->BW * 3;
+  const dim3 grid((units + 255) / 256, (c->BH + COMPOSE_ROWS - 1) / COMPOSE_ROWS, batch);
+  if (wide) k_compose_slabs<8><<<grid, 256, 0, c->stream>>>(a);
+  else k_compose_slabs<1><<<grid, 256, 0, c->stream>>>(a);
   LAUNCHED(c);
   return BEVK_OK;
 }

@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(256) k_lum_apply(const uint8_t* const* __restr
 // is not converted (about 17 % of a frame at the fixture geometry, 4.6x fewer HSV round trips
 // than converting the four taps of every output pixel).  grid = (FH, n_frames).
 // ---------------------------------------------------------------------------------
-constexpr int LUM_ROWS = 8;   // source rows per CTA: the 2 KB division tables are staged once per 8 rows, not once per row
+constexpr int LUM_ROWS = 1;   // source rows per CTA (8 measured 6 % slower than 1: the kernel is latency-, not prologue-bound)
 
 __global__ void __launch_bounds__(128) k_lum_spans(const uint8_t* const* __restrict__ frames, uint8_t* const* __restrict__ outs,
                                                    const int2* __restrict__ spans, int n_cam, int w, int h,

@@ -55,34 +55,41 @@ struct ComposeArgs {
 };
 
 #ifdef __CUDACC__
-// grid (chunks of 256 units per canvas row, canvas rows, frame-sets): no index arithmetic beyond adds.  WORD: canvas rows
-// are whole 32-bit words (BW % 4 == 0) and every slab edge falls on a word boundary (tile-aligned x, or the canvas edge)
-// -> a unit is 4 bytes; otherwise one byte.
-template <bool WORD>
+// grid (chunks of 256 units per canvas row, groups of COMPOSE_ROWS canvas rows, frame-sets): no index arithmetic beyond
+// adds.  UNIT bytes per thread and row: 8 when canvas rows are whole 8-byte words (BW % 8 == 0; every slab edge then falls
+// on an 8-byte boundary: tile-aligned x is a multiple of 96 bytes, the canvas edge a multiple of 8), else 1.
+constexpr int COMPOSE_ROWS = 4;
+
+template <int UNIT>
 __global__ void __launch_bounds__(256) k_compose_slabs(ComposeArgs a) {
-  const int b = blockIdx.z, y = blockIdx.y;
+  const int b = blockIdx.z;
   const int row_bytes = a.BW * 3;
-  const int xb = (blockIdx.x * 256 + threadIdx.x) * (WORD ? 4 : 1);
+  const int xb = (blockIdx.x * 256 + threadIdx.x) * UNIT;
   if (xb >= row_bytes) return;
-  const size_t off = (size_t)y * row_bytes + xb;
-  unsigned v = 0;
-#pragma unroll
-  for (int r = 0; r < SHARD_MAX_RANKS; ++r) {
-    if (r >= a.world) break;
-    const SlabRect q = a.rect[r];
-    if (y < q.oy || y >= q.oy1 || xb < q.ox * 3 || xb >= q.ox1 * 3) continue;
-    const uint8_t* p = a.slabs + (size_t)r * a.rank_stride + (size_t)b * a.slab_bytes + (size_t)(y - q.oy) * ((q.ox1 - q.ox) * 3) + (xb - q.ox * 3);
-    // plain loads (not the read-only path): in peer-store mode other GPUs wrote this memory
-    if (WORD) v = __vaddus4(v, *reinterpret_cast<const unsigned*>(p));
-    else v = min(255u, v + *p);
-  }
-  if (a.car) {
-    if (WORD) v = __vaddus4(v, __ldg(reinterpret_cast<const unsigned*>(a.car + off)));
-    else v = min(255u, v + __ldg(a.car + off));
-  }
   uint8_t* out = a.out + (size_t)b * row_bytes * a.BH;
-  if (WORD) *reinterpret_cast<unsigned*>(out + off) = v;
-  else out[off] = (uint8_t)v;
+#pragma unroll
+  for (int dy = 0; dy < COMPOSE_ROWS; ++dy) {
+    const int y = blockIdx.y * COMPOSE_ROWS + dy;
+    if (y >= a.BH) break;
+    const size_t off = (size_t)y * row_bytes + xb;
+    unsigned lo = 0, hi = 0;
+#pragma unroll
+    for (int r = 0; r < SHARD_MAX_RANKS; ++r) {
+      if (r >= a.world) break;
+      const SlabRect q = a.rect[r];
+      if (y < q.oy || y >= q.oy1 || xb < q.ox * 3 || xb >= q.ox1 * 3) continue;
+      const uint8_t* p = a.slabs + (size_t)r * a.rank_stride + (size_t)b * a.slab_bytes + (size_t)(y - q.oy) * ((q.ox1 - q.ox) * 3) + (xb - q.ox * 3);
+      // plain loads (not the read-only path): in peer-store mode other GPUs wrote this memory
+      if (UNIT == 8) { const uint2 v = *reinterpret_cast<const uint2*>(p); lo = __vaddus4(lo, v.x); hi = __vaddus4(hi, v.y); }
+      else lo = min(255u, lo + *p);
+    }
+    if (a.car) {
+      if (UNIT == 8) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(a.car + off)); lo = __vaddus4(lo, v.x); hi = __vaddus4(hi, v.y); }
+      else lo = min(255u, lo + __ldg(a.car + off));
+    }
+    if (UNIT == 8) *reinterpret_cast<uint2*>(out + off) = make_uint2(lo, hi);
+    else out[off] = (uint8_t)lo;
+  }
 }
 #endif
 
