@@ -33,13 +33,17 @@ using namespace bevk;
 // k_bev_tma configurations built into the library: FS = bytes of one frame-set's staged source box (a ring slot holds 4 FS
 // of boxes), STAGES = ring slots, MINCTAS = resident CTAs per SM the register budget is set for, EG = LUT-entry groups per
 // slot (the plan's items never span more).  The first entry is the default; BEVK_TMA_CFG="<FS>,<STAGES>,<EG>" (read at
-// bevk_bev_finalize) selects another one for tuning runs.
-#define BEVK_TMA_CONFIGS(X) X(4096, 2, 2, 4) X(6144, 2, 2, 2) X(4096, 3, 2, 2) X(4096, 2, 3, 2) X(5120, 3, 2, 2)
+// bevk_bev_finalize) selects another one for tuning runs.  Measured on B200 (profiles/r02_*stage_sweep*): with two CTAs per
+// SM the largest slots that fit win (fewer, fuller slots: 0.121 ms at FS 4096 -> 0.109 ms at FS 7936); a third, smaller
+// stage does not pay.  7936: 2 x (2 x 48256 + 16896 + 1056) + static/reserved = 233024 of the SM's 233472 bytes.
+#define BEVK_TMA_CONFIGS(X) X(7936, 2, 2, 4) X(7680, 2, 2, 4) X(6144, 2, 2, 4) X(5120, 2, 2, 4) X(4096, 2, 2, 4) X(4096, 3, 2, 2) X(4096, 2, 3, 2)
 struct TmaConfig { int fs, stages, min_ctas, eg; };
 #define X(FS, ST, MC, EG) {FS, ST, MC, EG},
 static const TmaConfig kTmaConfigs[] = {BEVK_TMA_CONFIGS(X)};
 #undef X
 static const int kNumTmaConfigs = (int)(sizeof kTmaConfigs / sizeof kTmaConfigs[0]);
+constexpr int kMaxTmaConfigs = 8;   // bevk_ctx::tma_grid
+static_assert(sizeof kTmaConfigs / sizeof kTmaConfigs[0] <= kMaxTmaConfigs, "grow bevk_ctx::tma_grid");
 
 
 // ------------------------------------------------------------------ errors
@@ -168,7 +172,7 @@ struct bevk_ctx {
   unsigned long long map_clock = 0;
   int tma_cfg = 0;                          // index into kTmaConfigs
   int tma_backoff_ns = 0;                   // BEVK_TMA_BACKOFF (read at finalize): producer poll interval when the ring is full
-  int tma_grid[8][4] = {};                  // [config] resident CTAs of k_bev_tma<BAL, NB>: index = 2*BAL + {NB=1:0, 4:1}
+  int tma_grid[kMaxTmaConfigs][4] = {};                  // [config] resident CTAs of k_bev_tma<BAL, NB>: index = 2*BAL + {NB=1:0, 4:1}
   DevBuf d_stack_ptrs;                      // pointer table of a frame stack (BALANCE pre-passes read frames through a table)
   const void* stack_ptrs_base = nullptr; long long stack_ptrs_stride = 0, stack_ptrs_n = 0;
   int last_path = 0;                        // 1: k_bev (pointer-table gather), 2: k_bev_tma
@@ -714,8 +718,9 @@ int bevk_bev_finalize(bevk_ctx* c) {
     const char* env = getenv("BEVK_TMA");
     const bool want = !(env && atoi(env) == 0) && ((unsigned)FW * 3u) % 16u == 0;
     if (want) {
+      const char* mm = getenv("BEVK_TMA_MAXMULT");   // tuning: largest multi-pass box (1, 2 or 4 FS); larger boxes become GATHER items
       build_tma_plan(NC, FW, FH, BW, BH, c->bev_interp == BEVK_INTER_NEAREST, p1.data(), p2.data(), pm.data(), c->tma_stage_bytes, true, tp,
-                     kTmaConfigs[c->tma_cfg].eg);
+                     kTmaConfigs[c->tma_cfg].eg, mm ? std::max(1, std::min(4, atoi(mm))) : 4);
       RET(c->d_ttiles.ensure(tp.tiles.size() * sizeof(int4)));
       RET(c->d_titems.ensure(std::max<size_t>(1, tp.items.size()) * sizeof(TmaItem)));
       RET(c->d_tlut.ensure(std::max<size_t>(1, tp.lut.size()) * sizeof(uint4)));
@@ -884,10 +889,33 @@ static int launch_bev_tma(bevk_ctx* c, const TmaParams& P, int nbu, bool bal) {
   const TmaConfig cfg = kTmaConfigs[c->tma_cfg];
   const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(units, c->tma_grid[c->tma_cfg][variant]));
   const size_t smem = bev_tma_smem_bytes(nbu, cfg.fs, cfg.stages, cfg.eg);
-  void* args[] = {const_cast<TmaParams*>(&P)};
   const bool scatter = P.world != 0;   // peer-store output: only without BALANCE (run_device checks)
+#ifdef BEVK_TRACE
+  // slot timeline (tools/gpu/trace_slots.py): the 12th launch of the process records clock64 stamps of the first 8 CTAs
+  // into BEVK_TRACE_FILE; a -DBEVK_TRACE build is for this measurement only
+  static unsigned long long* d_trace = nullptr;
+  static int n_launch = 0;
+  constexpr size_t kTraceWords = 8 * 512 * 8;
+  TmaParams PT = P;
+  const char* trace_file = getenv("BEVK_TRACE_FILE");
+  if (trace_file) {
+    if (!d_trace) CU(cudaMalloc(&d_trace, kTraceWords * 8));
+    if (++n_launch == 12) { CU(cudaMemsetAsync(d_trace, 0, kTraceWords * 8, c->stream)); PT.trace = d_trace; }
+  }
+  void* args[] = {&PT};
+#else
+  void* args[] = {const_cast<TmaParams*>(&P)};
+#endif
   CU(cudaLaunchKernel(tma_fns(c->tma_cfg).fn[scatter ? 4 + (nbu == 4 ? 1 : 0) : variant], dim3(blocks), dim3(TMA_THREADS), args, smem, c->stream));
   LAUNCHED(c);
+#ifdef BEVK_TRACE
+  if (trace_file && n_launch == 12) {
+    CU(cudaStreamSynchronize(c->stream));
+    std::vector<unsigned long long> h(kTraceWords);
+    CU(cudaMemcpy(h.data(), d_trace, kTraceWords * 8, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(trace_file, "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+  }
+#endif
   return BEVK_OK;
 }
 

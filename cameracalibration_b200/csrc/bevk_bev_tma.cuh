@@ -23,17 +23,22 @@
 //     global loads of the round-1 kernel.
 //
 // LUT entry (16 B, thread order t = warp*32 + lane, group k: canvas line k*8 + warp, position lane along it):
-//   .x  TMA item: byte offset of the aligned word holding tap (sy,sx) inside the frame-set's staged box | the same
-//       for row sy+1 << 16;   GATHER item: byte offset of tap (sy,sx) in the frame (slow entries: sx | sy << 16)
 //   .y  w00' | w10' << 16,  .z  w01' | w11' << 16   with w' = min(64 w, 65535): the DP2A sums carry
 //       64 (sum w p + 512), so byte 2 of each sum is the interpolated channel -- no shifts
+//   TMA item (every field is where one instruction finds it):
+//   .x  byte offset of the aligned word holding tap (sy,sx) inside the frame-set's staged box; row sy+1 lies one box
+//       pitch (slot descriptor) further
+//   .w  16-bit blend multiplier (bits 0..15, third DP2A operand as it is) | its rounding byte (16..23) |
+//       8 * (3 sx mod 4) = funnel-shift amount (24..28) | T_ACTIVE | T_THIRD (the tap pair starts at byte 3 of its word)
+//   GATHER item (boxes that fit no stage, ~1 % of the entries; the round-1 layout):
+//   .x  byte offset of tap (sy,sx) in the frame (slow entries: sx | sy << 16)
 //   .w  blend multiplier 257*mask+1 (17 bits) | (3 sx mod 4) << 17 | fraction << 19 | T_ACTIVE | T_SLOW
 #pragma once
 #include "bevk_bev.cuh"
 
 namespace bevk {
 
-constexpr unsigned T_ACTIVE = 1u << 29, T_SLOW = 1u << 30;
+constexpr unsigned T_ACTIVE = 1u << 29, T_SLOW = 1u << 30 /* GATHER entries */, T_THIRD = 1u << 30 /* TMA entries */;
 constexpr int ITEM_GATHER = 1, ITEM_NOSAT = 2, ITEM_FULL = 4;
 constexpr int TMA_CONSUMERS = 256, TMA_THREADS = TMA_CONSUMERS + 32;
 constexpr int TMA_DESC_BYTES = 128;   // sizeof(CUtensorMap)
@@ -46,7 +51,7 @@ struct __align__(16) TmaItem {   // 32 B, read as two 16-byte words
   int y;                         // ... and row; TMA zero-fills what lies outside the frame
   unsigned tx_bytes;             // bytes the box of ONE frame-set delivers
   int fs_bytes;                  // stage bytes reserved per frame-set: FS, 2 FS or 4 FS (a stage holds 4, 2 or 1 frame-sets)
-  int pad1;
+  int pitch;                     // row pitch of the staged box in bytes
 };
 static_assert(sizeof(TmaItem) == 32, "TmaItem is read as two int4");
 
@@ -74,6 +79,7 @@ struct TmaParams {
   uint8_t* peer[8];
   int world;
   long long src_off;
+  unsigned long long* trace;     // -DBEVK_TRACE builds (tools/gpu/trace_slots.py): [cta < 8][slot < 512][8] clock64 stamps; else unused
 };
 
 // The six words of one entry -> three sums whose byte 2 is the interpolated channel.
@@ -104,6 +110,24 @@ __host__ __device__ __forceinline__ unsigned interp_v(unsigned sh8, unsigned wl,
   interp_sums(sh8, wl, wr, a0, a1, a2, b0, b1, b2, sb, sg, sr);
   return weight_pack<false>(sb, sg, sr, wm);
 }
+
+// The same blend weight as ONE DP2A per channel (TMA entries).  The interpolated channel p is byte 2 of its sum and
+// byte 3 is 0 (the sums stay below 2^24), so dp2a_hi(ew, s, c) = (ew & 0xffff) * p + c whatever bits 16..31 of ew hold:
+//   mask < 255:  multiplier 257 mask + 1 (< 65536), c = 0    -> byte 2 = (p (257 mask + 1)) >> 16, the reference's value
+//   mask = 255:  multiplier 65535, c = 255                    -> 65535 p + 255 = 65536 p + (255 - p): byte 2 = p
+// (exhaustive check over all (p, mask): tests/host/kernel_math.cu).  .w of a TMA entry, fields as tma_item reads them:
+__host__ __device__ __forceinline__ unsigned tma_entry_w(unsigned mask, unsigned sh /* 3 sx mod 4 */) {
+  return (mask == 255u ? 65535u | (255u << 16) : mask * 257u + 1u) | (sh * 8u) << 24 | (sh == 3u ? T_THIRD : 0u) | T_ACTIVE;
+}
+template <bool FULL>
+__host__ __device__ __forceinline__ unsigned weight_pack16(unsigned sb, unsigned sg, unsigned sr, unsigned ew, unsigned c) {
+  if (FULL) return lane_perm(lane_perm(sb, sg, 0x0062), sr, 0x7610);
+  const unsigned ob = lane_dp2a_hi(ew, sb, c), og = lane_dp2a_hi(ew, sg, c), orr = lane_dp2a_hi(ew, sr, c);   // < 2^24
+  return lane_perm(lane_perm(ob, og, 0x0062), orr, 0x7610);
+}
+// fields of a TMA entry's .w: funnel-shift amount (the shifter uses bits 0..4 only), rounding byte
+__host__ __device__ __forceinline__ unsigned tma_entry_shift(unsigned ew) { return ew >> 24; }
+__host__ __device__ __forceinline__ unsigned tma_entry_round(unsigned ew) { return lane_perm(ew, 0u, 0x4442); }
 
 // DP2A weight pairs of a 10-bit fraction (fy*32 + fx), scaled by 64 (see header)
 __host__ __device__ __forceinline__ void scaled_weights(unsigned frac, unsigned& wl, unsigned& wr) {
@@ -178,6 +202,12 @@ __device__ __forceinline__ unsigned lds32_if(unsigned addr, unsigned pred) {
   return v;
 }
 __device__ __forceinline__ void sts32(unsigned addr, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  unsigned p;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory"); }
 
 // ring slot: boxes (4 FS) | LUT entries of up to EG groups (EG * 4 KB) | descriptor (128 B reserved)
@@ -186,9 +216,26 @@ constexpr size_t bev_tma_smem_bytes(int nb, int fs, int stages, int eg) {
   return (size_t)stages * slot_bytes(fs, eg) + (size_t)nb * ACC_WORDS * 4 + (size_t)stages * 16 + 1024;   // + alignment slack
 }
 
-// slot descriptor, word 0
+// Slot descriptor: two 16-byte words written by the producer, everything pre-digested so that a consumer warp spends a
+// handful of instructions per slot.
+//   word 0  .x flags (below) | groups in the slot << 16 | pass kind << 20 (0: four boxes FS apart, 1: two boxes 2 FS
+//              apart, 2: one box)
+//           .y row pitch of the staged boxes in bytes
+//           .z byte offset of the slot's first accumulator word relative to the thread's own (first group, first
+//              frame-set of the pass)
+//           .w accumulator bytes between consecutive groups
+//   word 1  (read by GATHER slots and by the slot that ends a unit)
+//           .x tile x | y << 16, .y first frame-set of the unit | frame-sets in it << 16, .z camera
 constexpr unsigned D_END = 1u, D_GATHER = 2u, D_FIRST = 4u, D_FULL = 8u, D_NOSAT = 16u, D_ORIENT = 32u, D_SYNC = 64u, D_LAST = 128u,
-                   D_NONE = 256u;   // bits 16..19: groups in the slot, 20..22: frame-sets of the pass, 24..26: first frame-set of the pass
+                   D_NONE = 256u, D_ROWS = 512u;
+// Barriers among the consumer warps.  Warp w accumulates canvas rows w, w+8, w+16, w+24 of the tile when the lanes run
+// along canvas x (orientation 0) and columns w, w+8, ... when they run along y; the interior write-out gives warp w the
+// rows w, w+8, w+16, w+24.  So a unit whose items all have orientation 0 never lets a warp touch another warp's words:
+//   * D_SYNC (barrier before the slot is applied): the orientation changes inside a unit, or the unit's first item has
+//     orientation 1 (other warps may still be writing out the rows it stores into), or the previous unit left through
+//     the generic write-out (edge tiles, BALANCE), which reads across rows;
+//   * D_ROWS on the slot that ends a unit: every item had orientation 0 and the tile takes the interior write-out --
+//     no barrier before the write-out either.  Otherwise the warps meet once before they write.
 
 // GATHER items (boxes that do not fit a stage): one entry applied to the NB frame-sets of the unit, taps from global
 // memory as in the round-1 kernel.  `aa`: shared address of the entry's accumulator word of frame-set 0.
@@ -233,10 +280,10 @@ __device__ __forceinline__ void gather_entry(const TmaParams& P, const uint4 e, 
 }
 
 // TMA slots: `nk` groups of LUT entries (in the slot, `ent` = this thread's first entry) applied to NBP staged boxes.
-// RS: slot bytes between the boxes of consecutive frame-sets.  FIRST: this camera stores (zeros where its mask is 0),
-// later cameras add; FULL: every weight of the item is 255.
+// RS: slot bytes between the boxes of consecutive frame-sets; `pitch`: bytes between the rows of a box.  FIRST: this
+// camera stores (zeros where its mask is 0), later cameras add; FULL: every weight of the item is 255.
 template <int NBP, int RS, bool FIRST, bool FULL, bool HALVES, bool NOSAT>
-__device__ __forceinline__ void tma_item(unsigned ent, int nk, unsigned sbase, unsigned aa, unsigned astep) {
+__device__ __forceinline__ void tma_item(unsigned ent, int nk, unsigned sbase, unsigned pitch, unsigned aa, unsigned astep) {
   uint4 nxt = lds128(ent);
 #pragma unroll 1
   for (int k = 0; k < nk; ++k, aa += astep) {
@@ -250,8 +297,8 @@ __device__ __forceinline__ void tma_item(unsigned ent, int nk, unsigned sbase, u
       }
       continue;
     }
-    const unsigned o0 = sbase + (e.x & 0xffffu), o1 = sbase + (e.x >> 16);
-    const unsigned sh8 = (e.w >> 14) & 24u, wm = e.w & 0x1ffffu, third = sh8 == 24u;
+    const unsigned o0 = sbase + e.x, o1 = o0 + pitch;
+    const unsigned sh = tma_entry_shift(e.w), third = e.w & T_THIRD, c = FULL ? 0u : tma_entry_round(e.w);
     // HALVES (3 CTAs per SM configurations): two frame-sets at a time, 12 words in flight, to stay inside 72 registers
     constexpr int G = HALVES && NBP > 2 ? 2 : NBP;
 #pragma unroll
@@ -266,8 +313,8 @@ __device__ __forceinline__ void tma_item(unsigned ent, int nk, unsigned sbase, u
 #pragma unroll
       for (int j = 0; j < G; ++j) {
         unsigned sb, sg, sr;
-        interp_sums(sh8, e.y, e.z, a0[j], a1[j], a2[j], b0[j], b1[j], b2[j], sb, sg, sr);
-        unsigned v = weight_pack<FULL>(sb, sg, sr, wm);
+        interp_sums(sh, e.y, e.z, a0[j], a1[j], a2[j], b0[j], b1[j], b2[j], sb, sg, sr);
+        unsigned v = weight_pack16<FULL>(sb, sg, sr, e.w, c);
         if (!FIRST) {
           const unsigned old = lds32(aa + (h + j) * ACC_WORDS * 4);
           v = NOSAT ? v + old : sat_add_bgr(v, old);                      // cv2.add chain, reference camera order
@@ -280,13 +327,13 @@ __device__ __forceinline__ void tma_item(unsigned ent, int nk, unsigned sbase, u
 
 // one pass of a TMA item: NBP frame-sets whose boxes lie RS bytes apart in the slot
 template <int NBP, int RS, bool HALVES>
-__device__ __forceinline__ void tma_pass(unsigned ent, int nk, unsigned sbase, unsigned aa, unsigned astep, bool first, bool full,
-                                         bool nosat) {
-  if (!first) {   // NOSAT: the masks of the tile sum to <= 255 everywhere (always so for the reference's blend masks): plain add
-    if (nosat) tma_item<NBP, RS, false, false, HALVES, true>(ent, nk, sbase, aa, astep);
-    else tma_item<NBP, RS, false, false, HALVES, false>(ent, nk, sbase, aa, astep);
-  } else if (NBP == 4 && full) tma_item<NBP, RS, true, true, HALVES, true>(ent, nk, sbase, aa, astep);
-  else tma_item<NBP, RS, true, false, HALVES, true>(ent, nk, sbase, aa, astep);
+__device__ __forceinline__ void tma_pass(unsigned ent, int nk, unsigned sbase, unsigned pitch, unsigned aa, unsigned astep,
+                                         unsigned flags) {
+  if (!(flags & D_FIRST)) {   // NOSAT: the masks of the tile sum to <= 255 everywhere (always so for the reference's blend masks): plain add
+    if (flags & D_NOSAT) tma_item<NBP, RS, false, false, HALVES, true>(ent, nk, sbase, pitch, aa, astep);
+    else tma_item<NBP, RS, false, false, HALVES, false>(ent, nk, sbase, pitch, aa, astep);
+  } else if (NBP == 4 && (flags & D_FULL)) tma_item<NBP, RS, true, true, HALVES, true>(ent, nk, sbase, pitch, aa, astep);
+  else tma_item<NBP, RS, true, false, HALVES, true>(ent, nk, sbase, pitch, aa, astep);
 }
 
 // where frame-set b of the call is written: the caller's buffer, or (scattered mode) the owning rank's slab buffer
@@ -294,6 +341,27 @@ template <bool SCATTER>
 __device__ __forceinline__ uint8_t* out_base(const TmaParams& P, int b) {
   if (!SCATTER) return P.out + (size_t)b * P.canvas_bytes;
   return P.peer[b % P.world] + P.src_off + (size_t)(b / P.world) * P.canvas_bytes;
+}
+
+// interior write-out of one lane: `rows` row pieces (one 32-bit word each, tile rows w, w+8, w+16, w+24 of warp w) of
+// `nb` frame-sets, the first at byte offset `off` of frame-set b0's output; wacc/wsel: the lane's accumulator word pair
+// and byte selector (k_bev_tma).  WHOLE: four rows, NB frame-sets, at least one camera -- the common case, without
+// per-word checks.
+template <int NB, bool SCATTER, bool CAR, bool WHOLE>
+__device__ __forceinline__ void tile_rows_out(const TmaParams& P, unsigned wacc, unsigned wsel, size_t off, int rows, int b0, int nb, bool none) {
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    if (!WHOLE && j >= nb) break;
+    uint8_t* o = out_base<SCATTER>(P, b0 + j) + off;   // SCATTER: straight into the owning rank over NVLink
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (!WHOLE && i >= rows) break;
+      const unsigned ra = wacc + (unsigned)(i * 8 * ACC_WPITCH * 4 + j * ACC_WORDS * 4);
+      unsigned v = (!WHOLE && none) ? 0u : lane_perm(lds32(ra), lds32(ra + 4), wsel);
+      if (CAR) v = lane_addus4(v, __ldg(reinterpret_cast<const unsigned*>(P.car + off + (size_t)i * 8 * P.out_pitch)));
+      *reinterpret_cast<unsigned*>(o + (size_t)i * 8 * P.out_pitch) = v;
+    }
+  }
 }
 
 // EG: LUT-entry groups a ring slot can hold (the plan's items never have more)
@@ -326,20 +394,36 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
   if (t >= TMA_CONSUMERS) {
     // ---------------- producer: one thread turns the plan into ring slots and stays STAGES slots ahead of the consumers
     if (t == TMA_CONSUMERS) {
-      unsigned n = 0;
-      auto post = [&](uint4 d0, unsigned cam, unsigned tx, const void* ent_src, unsigned ent_bytes, const uint8_t* map, int np,
-                      int rs, int bx, int by, int z0) {
-        const unsigned s = n % STAGES, ph = (n / STAGES) & 1u;
+      unsigned s = 0, ph = 0;   // ring position: slot, phase of its barriers
+#ifdef BEVK_TRACE
+      unsigned tn = 0;
+#endif
+      auto post = [&](uint4 d0, uint4 d1, unsigned tx, const void* ent_src, unsigned ent_bytes, const uint8_t* map, int np, int rs,
+                      int bx, int by, int z0) {
         const unsigned slot = stage0 + s * SLOT, full = bar_full + 8 * s;
+#ifdef BEVK_TRACE
+        const bool tr = P.trace && blockIdx.x < 8 && tn < 512;
+        unsigned long long* T = P.trace + ((size_t)blockIdx.x * 512 + tn) * 8;
+        if (tr) T[0] = clock64();
+#endif
         mbar_wait_backoff(bar_empty + 8 * s, ph ^ 1u, P.backoff_ns);   // consumers have left this slot
+#ifdef BEVK_TRACE
+        if (tr) { T[1] = clock64(); T[6] = tx; T[7] = d0.x; }
+#endif
         sts128(slot + DESC_OFF, d0);
-        sts32(slot + DESC_OFF + 16, cam);
+        sts128(slot + DESC_OFF + 16, d1);
         if (tx) mbar_expect_tx(full, tx); else mbar_arrive(full);
         if (ent_bytes) bulk_copy(slot + ENT_OFF, ent_src, ent_bytes, full);
         for (int j = 0; j < np; ++j) tma_load_3d(slot + j * rs, map, bx, by, z0 + j * P.n_cam, full);
-        ++n;
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+#ifdef BEVK_TRACE
+        if (tr) T[2] = clock64();
+        ++tn;
+#endif
       };
       const bool filtered = P.cam_lo > 0 || P.cam_hi < 8;   // BEVK_MAX_CAMERAS
+      const bool words_ok = !BAL && (P.out_pitch & 3) == 0 && (P.canvas_bytes & 3) == 0 && (P.ox & 3) == 0;   // as the consumers decide
+      bool prev_generic = false;   // the previous unit left through the generic write-out (reads across the warps' rows)
       // Units are handed out dynamically (one atomic per unit, only this thread needs it: the consumers follow the ring):
       // unit u = tile u / groups of the cost-sorted tile list, frame-set group u % groups -- heavy tiles first, so the
       // CTAs finish together.  The next unit's id and tile record are fetched while the current unit is being posted.
@@ -350,7 +434,8 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
         const int4 next_tile = next_unit < n_units ? __ldg(P.tiles + (int)(next_unit / groups)) : make_int4(0, 0, 0, 0);
         const int b0 = (int)(unit % groups) * NB;
         const int nb = min(NB, P.batch - b0);
-        const unsigned dz = (unsigned)tile.x | ((unsigned)tile.y << 16), dw = (unsigned)b0 | ((unsigned)nb << 16);
+        uint4 d1 = make_uint4((unsigned)tile.x | ((unsigned)tile.y << 16), (unsigned)b0 | ((unsigned)nb << 16), 0u, 0u);
+        const bool interior = words_ok && tile.x + TILE <= P.ox1;   // row-wise write-out: warp w reads its own rows only
         // last item of this unit that belongs to a camera of the call
         int last_it = tile.z + tile.w - 1;
         if (filtered)
@@ -360,10 +445,13 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
           }
         if (last_it < tile.z) {   // no camera of the call touches the tile (car hole, or another rank's cameras): zeros --
           // unless the tile lies outside the output window altogether (camera-sharded slabs): then there is nothing to do
-          if (!(tile.x >= P.ox1 || tile.x + TILE <= P.ox || tile.y >= P.oy1 || tile.y + TILE <= P.oy))
-            post(make_uint4(D_SYNC | D_LAST | D_NONE, 0u, dz, dw), 0u, 0u, nullptr, 0u, nullptr, 0, 0, 0, 0, 0);
+          if (!(tile.x >= P.ox1 || tile.x + TILE <= P.ox || tile.y >= P.oy1 || tile.y + TILE <= P.oy)) {
+            post(make_uint4((interior ? D_ROWS : D_SYNC) | D_LAST | D_NONE, 0u, 0u, 0u), d1, 0u, nullptr, 0u, nullptr, 0, 0, 0, 0, 0);
+            prev_generic = !interior;
+          }
         } else {
           int first_cam = -1, prev_orient = -1;
+          bool columns = false;   // an item of the unit ran its lanes along canvas y
           int4 n0 = __ldg(reinterpret_cast<const int4*>(P.items + tile.z));
           int4 n1 = __ldg(reinterpret_cast<const int4*>(P.items + tile.z) + 1);
           for (int it = tile.z; it <= last_it; ++it) {
@@ -376,95 +464,121 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
             if (cam < P.cam_lo || cam >= P.cam_hi) continue;
             const int k0 = i0.z & 0xff, nk = ((i0.z >> 8) & 0xff) - k0;
             unsigned f = 0;
-            if (first_cam < 0) { first_cam = cam; f |= D_SYNC; }               // the previous unit's write-out has read the accumulators
+            if (first_cam < 0) {   // other warps may still be writing out rows this item stores into (see D_SYNC above)
+              first_cam = cam;
+              if (orient || prev_generic) f |= D_SYNC;
+            }
+            columns |= orient != 0;
             if (cam == first_cam) f |= D_FIRST;                                // this camera stores, later ones add (cv2.add order)
             if (prev_orient >= 0 && prev_orient != orient) f |= D_SYNC;         // accumulator ownership changes with the orientation
             prev_orient = orient;
             if (orient) f |= D_ORIENT;
             if (iflags & ITEM_NOSAT) f |= D_NOSAT;
             if (iflags & ITEM_FULL) f |= D_FULL;
-            f |= (unsigned)nk << 16 | (unsigned)k0 << 28;
+            f |= (unsigned)nk << 16;
+            // accumulator walk of the item: lanes along canvas x -> a group is 8 rows; along y -> 8 columns
+            const unsigned astep = 4u * (unsigned)(orient ? 8 : 8 * ACC_WPITCH);
             const uint4* ent_src = P.lut + (size_t)i0.x * (TILE * TILE) + k0 * 256;
             const unsigned ent_bytes = (unsigned)nk * 4096u;
+            d1.z = (unsigned)cam;
             if (iflags & ITEM_GATHER) {
-              post(make_uint4(f | D_GATHER | (it == last_it ? D_LAST : 0u) | ((unsigned)nb << 20), 0u, dz, dw), (unsigned)cam, ent_bytes,
-                   ent_src, ent_bytes, nullptr, 0, 0, 0, 0, 0);
+              post(make_uint4(f | D_GATHER | (it == last_it ? D_LAST | (!columns && interior ? D_ROWS : 0u) : 0u), 0u, (unsigned)k0 * astep, astep),
+                   d1, ent_bytes, ent_src, ent_bytes, nullptr, 0, 0, 0, 0, 0);
               continue;
             }
             const uint8_t* map = P.maps + (size_t)((unsigned)i0.z >> 16) * TMA_DESC_BYTES;
             const int rs = i1.z, fpp = min(NB, SB / rs);                       // frame-sets per pass
+            f |= (fpp >= 4 ? 0u : (fpp == 2 ? 1u : 2u)) << 20;
             for (int p = 0; p < nb; p += fpp) {
               const int np = min(fpp, nb - p);
-              const unsigned fl = f | ((unsigned)np << 20) | ((unsigned)p << 24) | ((it == last_it && p + fpp >= nb) ? D_LAST : 0u);
-              post(make_uint4(p == 0 ? fl : (fl & ~D_SYNC), (unsigned)rs, dz, dw), (unsigned)cam, ent_bytes + (unsigned)np * (unsigned)i1.y,
+              const unsigned fl = (p == 0 ? f : (f & ~D_SYNC)) | ((it == last_it && p + fpp >= nb) ? D_LAST | (!columns && interior ? D_ROWS : 0u) : 0u);
+              post(make_uint4(fl, (unsigned)i1.w, (unsigned)k0 * astep + (unsigned)p * (ACC_WORDS * 4), astep), d1,
+                   ent_bytes + (unsigned)np * (unsigned)i1.y,
                    ent_src, ent_bytes, map, np, rs, i0.w, i1.x, (b0 + p) * P.n_cam + cam);
             }
           }
+          prev_generic = !interior;
         }
         unit = next_unit; tile = next_tile;
       }
-      post(make_uint4(D_END, 0u, 0u, 0u), 0u, 0u, nullptr, 0u, nullptr, 0, 0, 0, 0, 0);
+      post(make_uint4(D_END, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), 0u, nullptr, 0u, nullptr, 0, 0, 0, 0, 0);
     }
     return;
   }
 
   // ---------------- consumers: follow the ring; nothing below reads global memory except GATHER taps and the car overlay
-  const int posx = wrp * ACC_WPITCH + lane, stepx = 8 * ACC_WPITCH;   // lanes along canvas x: line k*8+wrp is a row
-  const int posy = lane * ACC_WPITCH + wrp, stepy = 8;                // lanes along canvas y: line k*8+wrp is a column
-  for (unsigned n = 0;; ++n) {
-    const unsigned s = n % STAGES, ph = (n / STAGES) & 1u;
+  const unsigned posx = acc_u32 + 4u * (unsigned)(wrp * ACC_WPITCH + lane);   // lanes along canvas x: line k*8+wrp is a row
+  const unsigned posy = acc_u32 + 4u * (unsigned)(lane * ACC_WPITCH + wrp);   // lanes along canvas y: line k*8+wrp is a column
+  const unsigned ent0 = stage0 + ENT_OFF + (unsigned)t * 16u;
+  const bool words_ok = !BAL && (P.out_pitch & 3) == 0 && (P.canvas_bytes & 3) == 0 && (P.ox & 3) == 0;
+  unsigned s = 0, ph = 0;
+#ifdef BEVK_TRACE
+  unsigned tn = 0;
+#endif
+  for (;;) {
     const unsigned slot = stage0 + s * SLOT;
+#ifdef BEVK_TRACE
+    const bool tr = P.trace && blockIdx.x < 8 && tn < 512 && t == 0;
+    unsigned long long* T = P.trace + ((size_t)blockIdx.x * 512 + tn) * 8;
+    ++tn;
+    if (tr) T[3] = clock64();
+#endif
     mbar_wait(bar_full + 8 * s, ph);                     // descriptor, entries and boxes of this slot have landed
+#ifdef BEVK_TRACE
+    if (tr) T[4] = clock64();
+#endif
     const uint4 d = lds128(slot + DESC_OFF);
     const unsigned flags = d.x;
     if (flags & D_END) break;
-    const int nk = (flags >> 16) & 15, p = (flags >> 24) & 7, k0 = (flags >> 28) & 3;
-    const bool first = (flags & D_FIRST) != 0, nosat = (flags & D_NOSAT) != 0;
-    const int4 tile = make_int4((int)(d.z & 0xffffu), (int)(d.z >> 16), 0, 0);
-    const int b0 = (int)(d.w & 0xffffu), nb = (int)(d.w >> 16);
     if (flags & D_SYNC) consumer_sync();
+    const int nk = (flags >> 16) & 15;
     if (nk) {
-      const bool orient = (flags & D_ORIENT) != 0;
-      const unsigned astep = 4u * (unsigned)(orient ? stepy : stepx);
-      const unsigned aa = acc_u32 + 4u * (unsigned)(orient ? posy : posx) + (unsigned)k0 * astep + (unsigned)p * (ACC_WORDS * 4);
-      const unsigned ent = slot + ENT_OFF + (unsigned)t * 16u;
+      const unsigned aa = ((flags & D_ORIENT) ? posy : posx) + d.z;
+      const unsigned ent = ent0 + s * SLOT;
       if (flags & D_GATHER) {
-        const int cam = (int)lds32(slot + DESC_OFF + 16);
-        const uint8_t* frame0 = P.base + (long long)(b0 * P.n_cam + cam) * P.frame_stride;
+        const uint4 d1 = lds128(slot + DESC_OFF + 16);
+        const int b0 = (int)(d1.y & 0xffffu), nb = (int)(d1.y >> 16);
+        const uint8_t* frame0 = P.base + (long long)(b0 * P.n_cam + (int)d1.z) * P.frame_stride;
         const long long set_stride = (long long)P.n_cam * P.frame_stride;
 #pragma unroll 1
-        for (int k = 0; k < nk; ++k) gather_entry<NB>(P, lds128(ent + k * 4096), aa + k * astep, first, nosat, frame0, set_stride, nb);
+        for (int k = 0; k < nk; ++k)
+          gather_entry<NB>(P, lds128(ent + k * 4096), aa + k * d.w, (flags & D_FIRST) != 0, (flags & D_NOSAT) != 0, frame0, set_stride, nb);
       } else {
-        const unsigned rs = d.y;
-        const bool full = (flags & D_FULL) != 0;
-        if (NB == 4 && rs == FS) tma_pass<(NB == 4 ? 4 : 1), FS, (MINCTAS > 2)>(ent, nk, slot, aa, astep, first, full, nosat);
-        else if (NB == 4 && rs == 2 * FS) tma_pass<(NB == 4 ? 2 : 1), 2 * FS, false>(ent, nk, slot, aa, astep, first, full, nosat);
-        else tma_pass<1, 0, false>(ent, nk, slot, aa, astep, first, full, nosat);
+        const unsigned kind = (flags >> 20) & 3u;
+        if (NB == 4 && kind == 0u) tma_pass<(NB == 4 ? 4 : 1), FS, (MINCTAS > 2)>(ent, nk, slot, d.y, aa, d.w, flags);
+        else if (NB == 4 && kind == 1u) tma_pass<(NB == 4 ? 2 : 1), 2 * FS, false>(ent, nk, slot, d.y, aa, d.w, flags);
+        else tma_pass<1, 0, false>(ent, nk, slot, d.y, aa, d.w, flags);
       }
     }
+    // word 1 (tile, frame-sets) is needed by the slot that ends a unit; it is read before this warp releases the slot
+    uint4 d1 = make_uint4(0u, 0u, 0u, 0u);
+    if (flags & D_LAST) d1 = lds128(slot + DESC_OFF + 16);
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_empty + 8 * s);       // this warp no longer reads the slot
+#ifdef BEVK_TRACE
+    if (tr) T[5] = clock64();
+#endif
+    if (elect_one()) mbar_arrive(bar_empty + 8 * s);     // this warp no longer reads the slot
+    if (++s == STAGES) { s = 0; ph ^= 1u; }
     if (!(flags & D_LAST)) continue;
+    // ---- the unit is complete: write the tile(s)
     const bool none = (flags & D_NONE) != 0;              // tile without a camera (car hole): zeros
-    consumer_sync();
-    // ---- write the tile(s)
+    if (!(flags & D_ROWS)) consumer_sync();               // other warps accumulated into the rows this warp writes
+    const int4 tile = make_int4((int)(d1.x & 0xffffu), (int)(d1.x >> 16), 0, 0);
+    const int b0 = (int)(d1.y & 0xffffu), nb = (int)(d1.y >> 16);
     if (tile.x >= P.ox1 || tile.x + TILE <= P.ox || tile.y >= P.oy1 || tile.y + TILE <= P.oy) continue;   // outside the output window
-    if (!BAL && tile.x + TILE <= P.ox1 && (P.out_pitch & 3) == 0 && (P.canvas_bytes & 3) == 0 && (P.ox & 3) == 0) {
-      // interior tile: 32 rows x 24 words, written as 3 x 256 consecutive words (a warp store = two 96-byte row pieces)
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int idx = i * 256 + t, r = idx / 24, w = idx - r * 24;
-        const int gy = tile.y + r;
-        if (gy >= P.oy1) continue;
-        const size_t word_off = ((size_t)(gy - P.oy) * P.out_pitch + (size_t)(tile.x - P.ox) * 3) / 4 + w;
-        const unsigned cw = P.car ? __ldg(reinterpret_cast<const unsigned*>(P.car) + word_off) : 0u;
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-          if (j >= nb) break;
-          unsigned v = none ? 0u : tile_row_word(acc + j * ACC_WORDS + r * ACC_WPITCH, w);
-          if (P.car) v = lane_addus4(v, cw);
-          reinterpret_cast<unsigned*>(out_base<SCATTER>(P, b0 + j))[word_off] = v;   // SCATTER: straight into the owning rank over NVLink
-        }
+    if (words_ok && tile.x + TILE <= P.ox1) {
+      // interior tile: warp w stores rows w, w+8, w+16, w+24, lanes 0..23 one packed-BGR word each (bytes 4l..4l+3 of a
+      // row start in BGRX word l + l/3 at byte phase l % 3): four 96-byte row pieces per frame-set and warp
+      if (lane < 24) {
+        const int wq = lane / 3, wph = lane - 3 * wq;
+        const unsigned wsel = wph == 0 ? 0x4210u : (wph == 1 ? 0x5421u : 0x6542u);
+        const unsigned wacc = acc_u32 + 4u * (unsigned)(wrp * ACC_WPITCH + lane + wq);
+        const int gy0 = tile.y + wrp;
+        const int rows = max(0, min(4, (P.oy1 - gy0 + 7) / 8));
+        const size_t off = (size_t)(gy0 - P.oy) * P.out_pitch + (size_t)(tile.x - P.ox) * 3 + (size_t)lane * 4;
+        if (P.car) tile_rows_out<NB, SCATTER, true, false>(P, wacc, wsel, off, rows, b0, nb, none);
+        else if (rows == 4 && nb == NB && !none) tile_rows_out<NB, SCATTER, false, true>(P, wacc, wsel, off, rows, b0, nb, none);
+        else tile_rows_out<NB, SCATTER, false, false>(P, wacc, wsel, off, rows, b0, nb, none);
       }
       continue;
     }
@@ -496,10 +610,10 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
         for (int q = 0; q < 4; ++q)
           if (q < npx) { sb += px[q] & 255u; sg += (px[q] >> 8) & 255u; sr += (px[q] >> 16) & 255u; }
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {   // every lane takes part (out-of-canvas lanes add 0)
-          sb += __shfl_xor_sync(0xffffffffu, sb, s);
-          sg += __shfl_xor_sync(0xffffffffu, sg, s);
-          sr += __shfl_xor_sync(0xffffffffu, sr, s);
+        for (int d = 16; d > 0; d >>= 1) {   // every lane takes part (out-of-canvas lanes add 0)
+          sb += __shfl_xor_sync(0xffffffffu, sb, d);
+          sg += __shfl_xor_sync(0xffffffffu, sg, d);
+          sr += __shfl_xor_sync(0xffffffffu, sr, d);
         }
         if (lane == 0) {
           atomicAdd(&s_sum[3 * j + 0], (unsigned long long)sb);

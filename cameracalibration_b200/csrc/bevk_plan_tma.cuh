@@ -65,7 +65,7 @@ inline int lds_wavefronts(const unsigned* word, int n) {
 
 inline void build_tma_plan(int NC, int FW, int FH, int BW, int BH, bool nearest, const short* const* m1,
                            const unsigned short* const* m2, const uint8_t* const* masks, int stage_bytes, bool allow_tma,
-                           TmaPlan& out, int max_groups = 4) {
+                           TmaPlan& out, int max_groups = 4, int max_mult = 4) {
   const unsigned pitch = (unsigned)FW * 3u;
   const long long frame_bytes = (long long)pitch * FH;
   const int tx = (BW + TILE - 1) / TILE, ty = (BH + TILE - 1) / TILE;
@@ -130,8 +130,10 @@ inline void build_tma_plan(int NC, int FW, int FH, int BW, int BH, bool nearest,
         // recursive partition of the groups [g0,g1)
         struct Range { int g0, g1; };
         std::vector<Range> todo;   // a ring slot holds the entries of at most max_groups groups
-        for (int g = 4 - std::max(1, std::min(4, max_groups)); g >= 0; g -= std::max(1, std::min(4, max_groups)))
-          todo.push_back({g, g + std::max(1, std::min(4, max_groups))});
+        {
+          const int mg = std::max(1, std::min(4, max_groups));
+          for (int g = ((4 - 1) / mg) * mg; g >= 0; g -= mg) todo.push_back({g, std::min(4, g + mg)});   // popped in group order
+        }
         std::vector<TmaItem> made;
         while (!todo.empty()) {
           const Range r = todo.back();
@@ -161,7 +163,7 @@ inline void build_tma_plan(int NC, int FW, int FH, int BW, int BH, bool nearest,
             const long long bytes = (long long)w16 * 16 * hh;
             fits = shape_ok && bytes <= stage_bytes;
             if (!fits && shape_ok && r.g1 - r.g0 == 1) {       // a single strip: give it 2 or 4 frame-set slots of the stage
-              for (int m = 2; m <= 4 && !fits; m *= 2)
+              for (int m = 2; m <= max_mult && !fits; m *= 2)
                 if (bytes <= (long long)m * stage_bytes && (long long)m * stage_bytes <= 65536) { fits = true; fs_bytes = m * stage_bytes; }
             }
           }
@@ -201,7 +203,7 @@ inline void build_tma_plan(int NC, int FW, int FH, int BW, int BH, bool nearest,
               if (out.shapes[s].x == w16 * 4 && out.shapes[s].y == hh) { shape = (int)s; break; }
             if (shape < 0) { shape = (int)out.shapes.size(); out.shapes.push_back(make_int2(w16 * 4, hh)); }
             it.shape = (unsigned short)shape; it.xw = bx0; it.y = ry0; it.tx_bytes = (unsigned)(w16 * 16 * hh);
-            it.fs_bytes = fs_bytes;
+            it.fs_bytes = fs_bytes; it.pitch = w16 * 16;
             out.box_bytes += it.tx_bytes;
             item_cost += (long long)n_act * (4 * stage_bytes / fs_bytes == 4 ? 10 : (fs_bytes == 2 * stage_bytes ? 13 : 18));
           } else {
@@ -216,8 +218,8 @@ inline void build_tma_plan(int NC, int FW, int FH, int BW, int BH, bool nearest,
             uint4 u;
             scaled_weights(e.frac, u.y, u.z);
             const int b = 3 * e.sx, w0 = floor_div(b, 4), sh = b - 4 * w0;
-            u.w = (e.w * 257u + 1u) | ((unsigned)sh << 17) | (e.frac << 19) | T_ACTIVE;
             if (it.flags & ITEM_GATHER) {
+              u.w = (e.w * 257u + 1u) | ((unsigned)sh << 17) | (e.frac << 19) | T_ACTIVE;
               const long long off = (long long)e.sy * pitch + (long long)e.sx * 3;
               const bool in_frame = e.sx >= 0 && e.sy >= 0 && e.sx + 1 < FW && e.sy + 1 < FH && !(pitch & 3u) &&
                                     off + pitch + 12 <= frame_bytes;
@@ -225,8 +227,8 @@ inline void build_tma_plan(int NC, int FW, int FH, int BW, int BH, bool nearest,
               else { u.w |= T_SLOW; u.x = (unsigned)(unsigned short)e.sx | ((unsigned)(unsigned short)e.sy << 16); }
               ++out.gather_entries;
             } else {
-              const unsigned o0 = (unsigned)((e.sy - ry0) * (w16 * 16) + (w0 - bx0) * 4);
-              u.x = o0 | ((o0 + (unsigned)(w16 * 16)) << 16);
+              u.x = (unsigned)((e.sy - ry0) * (w16 * 16) + (w0 - bx0) * 4);   // row sy + 1: one box pitch further
+              u.w = tma_entry_w(e.w, (unsigned)sh);
               ++out.tma_entries;
             }
             out.lut[base + i] = u;

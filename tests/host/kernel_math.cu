@@ -297,6 +297,7 @@ static int mode_bev(const char* in_path, const char* out_path, int tma_stage_byt
           memset(stage.data(), 0xEE, stage.size());
           const int2 shape = tp.shapes[item.shape];
           CHECK((unsigned)(shape.x * 4 * shape.y) == item.tx_bytes && (int)item.tx_bytes <= item.fs_bytes, "box bytes");
+          CHECK(item.pitch == shape.x * 4, "box pitch");
           CHECK(item.fs_bytes == tma_stage_bytes || ((item.fs_bytes == 2 * tma_stage_bytes || item.fs_bytes == 4 * tma_stage_bytes) &&
                                                      item.k1 - item.k0 == 1), "frame-set slot size");
           CHECK((item.xw & 3) == 0 && (shape.x & 3) == 0, "box alignment");
@@ -314,19 +315,26 @@ static int mode_bev(const char* in_path, const char* out_path, int tma_stage_byt
             unsigned v;
             if (gather && (e.w & T_SLOW)) {
               v = sample_slow_core(geo, src, e.x, (e.w & 0x1ffffu) | (((e.w >> 19) & 1023u) << 17));
-            } else {
+            } else if (gather) {   // round-1 entry layout, taps from the frame
               const unsigned sh8 = (e.w >> 14) & 24u, wm = e.w & 0x1ffffu;
               const bool third = sh8 == 24u;
-              const uint8_t *q0, *q1;
-              if (gather) { q0 = src + (e.x & ~3u); q1 = q0 + geo.pitch; }
-              else {
-                q0 = stage.data() + (e.x & 0xffffu); q1 = stage.data() + (e.x >> 16);
-                CHECK((e.x >> 16) + (third ? 12u : 8u) <= item.tx_bytes, "entry reads past its box");
-              }
+              const uint8_t *q0 = src + (e.x & ~3u), *q1 = q0 + geo.pitch;
               unsigned sb, sg, sr;
               interp_sums(sh8, e.y, e.z, ldg32(q0), ldg32(q0 + 4), third ? ldg32(q0 + 8) : 0u, ldg32(q1), ldg32(q1 + 4),
                           third ? ldg32(q1 + 8) : 0u, sb, sg, sr);
-              v = (item.flags & ITEM_FULL) && !gather ? weight_pack<true>(sb, sg, sr, wm) : weight_pack<false>(sb, sg, sr, wm);
+              v = weight_pack<false>(sb, sg, sr, wm);
+            } else {               // TMA entry: fields as tma_item decodes them, taps from the staged box
+              const unsigned sh = tma_entry_shift(e.w), c = tma_entry_round(e.w);
+              const bool third = (e.w & T_THIRD) != 0;
+              CHECK(third == ((sh & 31u) == 24u) && (sh & 7u) == 0, "entry shift / third-word flag");
+              CHECK(e.x % 4 == 0 && e.x + (unsigned)item.pitch + (third ? 12u : 8u) <= item.tx_bytes, "entry reads past its box");
+              const uint8_t *q0 = stage.data() + e.x, *q1 = q0 + item.pitch;
+              // a word the kernel does not load (predicated third word) is poison here: the result must not depend on it
+              unsigned sb, sg, sr;
+              interp_sums(sh, e.y, e.z, ldg32(q0), ldg32(q0 + 4), third ? ldg32(q0 + 8) : 0xA5A5A5A5u, ldg32(q1), ldg32(q1 + 4),
+                          third ? ldg32(q1 + 8) : 0x5A5A5A5Au, sb, sg, sr);
+              CHECK((sb >> 24) == 0 && (sg >> 24) == 0 && (sr >> 24) == 0, "interpolation sum reaches byte 3");
+              v = (item.flags & ITEM_FULL) ? weight_pack16<true>(sb, sg, sr, e.w, c) : weight_pack16<false>(sb, sg, sr, e.w, c);
             }
             *a = first ? v : (nosat ? v + *a : sat_add_bgr(v, *a));
           }
@@ -517,6 +525,20 @@ int main(int argc, char** argv) {
       const unsigned wm = m ? 257u * m + 1u : 0u;
       CHECK(((v * wm) >> 16) == (unsigned)(uint8_t)((float)v * fm), "identity v=%u m=%u", v, m);
     }
+  // ---- the same weight as k_bev_tma applies it: ONE DP2A per channel on the interpolation sum (byte 2 = value, byte 3 = 0,
+  //      bytes 0..1 = whatever the sum left there), 16-bit multiplier + rounding byte from the entry (tma_entry_w), for every
+  //      (value, mask > 0), every funnel shift, two settings of the sum's low bytes
+  for (unsigned v = 0; v < 256; ++v)
+    for (unsigned m = 1; m < 256; ++m)
+      for (unsigned sh = 0; sh < 4; ++sh)
+        for (unsigned low = 0; low < 2; ++low) {
+          const unsigned ew = tma_entry_w(m, sh), c = tma_entry_round(ew), sum = (v << 16) | (low ? 0xffffu : 0x0000u);
+          const unsigned want = (unsigned)(uint8_t)((float)v * (float)((double)m / 255.0));
+          const unsigned packed = weight_pack16<false>(sum, sum, sum, ew, c);
+          CHECK(packed == want * 0x010101u, "dp2a blend v=%u m=%u: %06x vs %02x", v, m, packed, want);
+          CHECK((tma_entry_shift(ew) & 31u) == 8u * sh && ((ew & T_THIRD) != 0) == (sh == 3u) && (ew & T_ACTIVE), "entry fields");
+          CHECK(weight_pack16<true>(sum, sum, sum, ew, 0u) == v * 0x010101u, "full-weight pack");
+        }
   // ---- sat_add_bgr / lane_addus4
   for (int i = 0; i < 2000000; ++i) {
     unsigned a = rnd() & 0x00ffffffu, b = rnd() & 0x00ffffffu;

@@ -23,8 +23,9 @@ def ops():
     return o
 
 
-def _engine(ops, fx, g, blend, calib=None, masks=None, tma=True, cams=None):
-    """BevEngine for geometry g; tma=False builds it with BEVK_TMA=0 (read at finalize): the gather kernel only."""
+def _engine(ops, fx, g, blend, calib=None, masks=None, tma=True, cams=None, env=None):
+    """BevEngine for geometry g; tma=False builds it with BEVK_TMA=0 (read at finalize): the gather kernel only.
+    env: further tuning variables bevk_bev_finalize reads (BEVK_TMA_CFG, BEVK_TMA_MAXMULT)."""
     calib = calib or fx.scaled_calib(g)
     cams = cams or [calib[n] for n in NAMES]
     e = ops.BevEngine(len(cams), (g.FW, g.FH), (g.BW, g.BH))
@@ -33,16 +34,49 @@ def _engine(ops, fx, g, blend, calib=None, masks=None, tma=True, cams=None):
     for i, (K, D, H) in enumerate(cams):
         e.set_camera(i, K, D, C.dst_camera_matrix(K, g.FW, g.FH, g.FS, g.SS), (int(g.FW * g.SS), int(g.FH * g.SS)), H)
         e.set_mask(i, masks[i])
-    old = os.environ.get("BEVK_TMA")
-    os.environ["BEVK_TMA"] = "1" if tma else "0"
+    want = dict(env or {}, BEVK_TMA="1" if tma else "0")
+    old = {k: os.environ.get(k) for k in want}
+    os.environ.update(want)
     try:
         e.finalize()
     finally:
-        if old is None:
-            os.environ.pop("BEVK_TMA", None)
-        else:
-            os.environ["BEVK_TMA"] = old
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     return e, masks
+
+
+@pytest.mark.parametrize("env", [
+    {"BEVK_TMA_CFG": "4096,2,4"},                               # smaller stage: 2- and 4-pass boxes (1 / 2 frame-sets per slot)
+    {"BEVK_TMA_CFG": "4096,2,4", "BEVK_TMA_MAXMULT": "1"},      # no multi-pass boxes: whatever exceeds a stage is a GATHER item
+    {"BEVK_TMA_CFG": "4096,3,2"},                               # three ring slots, two entry groups per slot
+    {"BEVK_TMA_CFG": "5120,2,4", "BEVK_TMA_MAXMULT": "2"},
+])
+def test_tma_kernel_other_configurations(ops, fx, env):
+    """The built-in alternative configurations and plan limits (tuning switches) run the same kernel code with other
+    template constants and other item mixes -- multi-pass items, GATHER items, a three-slot ring; the default's large
+    stage rarely produces those at test sizes.  cfg4 shape, blend, batch 6 (ragged tail), car: bytes equal to the
+    default configuration's."""
+    import torch
+    g = fx.geometry(1920, 1080, 1000, 1000)
+    e0, masks = _engine(ops, fx, g, True)
+    e1, _ = _engine(ops, fx, g, True, masks=masks, env=env)
+    i0, i1 = e0.tma_plan_info(), e1.tma_plan_info()
+    assert i1["items"] > 0 and (i1["items"], i1["gather_entries"]) != (i0["items"], i0["gather_entries"]), (i0, i1)
+    dev = torch.device("cuda", e0.ctx.device)
+    F = fx.frames(1920, 1080)
+    rng = np.random.default_rng(11)
+    sets = [F] + [[np.ascontiguousarray(np.roll(f, 31 * i + 7 * c, axis=1) ^ rng.integers(0, 32, f.shape, dtype=np.uint8))
+                   for c, f in enumerate(F)] for i in range(1, 6)]
+    d_all = _stack(torch, dev, sets)
+    car = torch.from_numpy(fx.car(1000, 1000)).to(dev)
+    for c in (None, car):
+        a = _run_stack(torch, e0, d_all, c)
+        b = _run_stack(torch, e1, d_all, c)
+        assert e0.last_path() == "tma" and e1.last_path() == "tma"
+        assert (a == b).all(), (env, int((a != b).sum()))
 
 
 def _stack(torch, dev, sets):

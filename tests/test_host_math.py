@@ -220,10 +220,11 @@ def _bev_on_host(exe, tmp_path, fx, g, calib, masks, frames, car, balance, neare
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     out = np.fromfile(tmp_path / "bev_out.bin", np.uint8).reshape(g.BH, g.BW, 3)
     # the TMA-staged kernel's plan (bevk_plan_tma.cuh) through its own interpreter: boxes modelled as the tensor copy
-    # delivers them (zeros outside the frame); three (stage size, entry groups per slot) settings: the shipped default,
-    # one that forces strip splits / multi-pass / GATHER items, one with single-group items
+    # delivers them (zeros outside the frame); several (stage size, entry groups per slot) settings: the shipped default,
+    # one that forces strip splits / multi-pass / GATHER items, three entry groups per slot (4 groups = 3 + 1), single-group
+    # items
     info = r.stdout
-    for stage, max_groups in ((4096, 2), (1536, 4), (6144, 1)):
+    for stage, max_groups in ((7936, 4), (1536, 4), (4096, 3), (6144, 1)):
         rt = subprocess.run([exe, "bevtma", str(tmp_path / "bev_in.bin"), str(tmp_path / "bevtma_out.bin"), str(stage), str(max_groups)],
                             capture_output=True, text=True, timeout=600)
         assert rt.returncode == 0, (rt.returncode, rt.stdout, rt.stderr)

@@ -1,0 +1,25 @@
+#!/bin/bash
+# round 2, call M2: L2 prefetch of the next item's boxes, slot timeline at the larger stage size
+cd "$GRAFT_REPO_ROOT" || exit 1
+O=gpurun_out/r2m2; mkdir -p $O
+B="timeout 300 python bench.py --no-cpu-baseline --e2e-steps 1 --steps 200 --warmup 5"
+run() { # name, env...
+  local name=$1; shift
+  env BEVK_BENCH_NO_API=1 "$@" $B > $O/bench_$name.json 2> $O/bench_$name.err
+  python - "$O/bench_$name.json" "$name" <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    t=d['plan']['tma']
+    print(sys.argv[2], 'ms/step', round(d['ms_per_step'],5), 'isolated', round(d['roofline']['kernel_ms_isolated'],5), 'same', d['e2e']['matches_device_path'], 'items', t['items'], 'gather', t['gather_entries'], 'box', t['box_bytes'])
+except Exception as e:
+    print(sys.argv[2], 'FAILED', e, open(sys.argv[1].replace('.json','.err')).read()[-300:])
+PY
+}
+L=$PWD/ab/libbevk_base5.so
+run f7936 BEVK_LIB_PATH=$L BEVK_TMA_CFG=7936,2,4
+run f7936_pf BEVK_LIB_PATH=$L BEVK_TMA_CFG=7936,2,4 BEVK_TMA_PREFETCH=1
+run f4096_pf BEVK_LIB_PATH=$L BEVK_TMA_PREFETCH=1
+run f5632 BEVK_LIB_PATH=$L BEVK_TMA_CFG=5632,2,4
+cat $O/bench_f5632.err | tail -3
+run trace BEVK_LIB_PATH=$PWD/ab/libbevk_trace5.so BEVK_TMA_CFG=7936,2,4 BEVK_TRACE_FILE=$PWD/$O/trace_7936.bin
