@@ -895,7 +895,7 @@ static int launch_bev_tma(bevk_ctx* c, const TmaParams& P, int nbu, bool bal) {
   // into BEVK_TRACE_FILE; a -DBEVK_TRACE build is for this measurement only
   static unsigned long long* d_trace = nullptr;
   static int n_launch = 0;
-  constexpr size_t kTraceWords = 8 * 512 * 8;
+  constexpr size_t kTraceWords = 8 * 512 * 16;
   TmaParams PT = P;
   const char* trace_file = getenv("BEVK_TRACE_FILE");
   if (trace_file) {

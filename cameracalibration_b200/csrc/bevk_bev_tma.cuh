@@ -79,7 +79,7 @@ struct TmaParams {
   uint8_t* peer[8];
   int world;
   long long src_off;
-  unsigned long long* trace;     // -DBEVK_TRACE builds (tools/gpu/trace_slots.py): [cta < 8][slot < 512][8] clock64 stamps; else unused
+  unsigned long long* trace;     // -DBEVK_TRACE builds (tools/gpu/trace_slots.py): [cta < 8][slot < 512][16] clock64 stamps; else unused
 };
 
 // The six words of one entry -> three sums whose byte 2 is the interpolated channel.
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
         const unsigned slot = stage0 + s * SLOT, full = bar_full + 8 * s;
 #ifdef BEVK_TRACE
         const bool tr = P.trace && blockIdx.x < 8 && tn < 512;
-        unsigned long long* T = P.trace + ((size_t)blockIdx.x * 512 + tn) * 8;
+        unsigned long long* T = P.trace + ((size_t)blockIdx.x * 512 + tn) * 16;
         if (tr) T[0] = clock64();
 #endif
         mbar_wait_backoff(bar_empty + 8 * s, ph ^ 1u, P.backoff_ns);   // consumers have left this slot
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
     const unsigned slot = stage0 + s * SLOT;
 #ifdef BEVK_TRACE
     const bool tr = P.trace && blockIdx.x < 8 && tn < 512 && t == 0;
-    unsigned long long* T = P.trace + ((size_t)blockIdx.x * 512 + tn) * 8;
+    unsigned long long* T = P.trace + ((size_t)blockIdx.x * 512 + tn) * 16;
     ++tn;
     if (tr) T[3] = clock64();
 #endif
@@ -559,10 +559,16 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
 #endif
     if (elect_one()) mbar_arrive(bar_empty + 8 * s);     // this warp no longer reads the slot
     if (++s == STAGES) { s = 0; ph ^= 1u; }
+#ifdef BEVK_TRACE
+    if (tr) T[8] = clock64();
+#endif
     if (!(flags & D_LAST)) continue;
     // ---- the unit is complete: write the tile(s)
     const bool none = (flags & D_NONE) != 0;              // tile without a camera (car hole): zeros
     if (!(flags & D_ROWS)) consumer_sync();               // other warps accumulated into the rows this warp writes
+#ifdef BEVK_TRACE
+    if (tr) T[9] = clock64();
+#endif
     const int4 tile = make_int4((int)(d1.x & 0xffffu), (int)(d1.x >> 16), 0, 0);
     const int b0 = (int)(d1.y & 0xffffu), nb = (int)(d1.y >> 16);
     if (tile.x >= P.ox1 || tile.x + TILE <= P.ox || tile.y >= P.oy1 || tile.y + TILE <= P.oy) continue;   // outside the output window
@@ -580,6 +586,9 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
         else if (rows == 4 && nb == NB && !none) tile_rows_out<NB, SCATTER, false, true>(P, wacc, wsel, off, rows, b0, nb, none);
         else tile_rows_out<NB, SCATTER, false, false>(P, wacc, wsel, off, rows, b0, nb, none);
       }
+#ifdef BEVK_TRACE
+      if (tr) T[10] = clock64();
+#endif
       continue;
     }
     // edge tiles and the BALANCE variant: thread t -> row t/8, 4 pixels (12 bytes) at pixel 4*(t%8)
