@@ -92,11 +92,19 @@ __host__ __device__ __forceinline__ unsigned interp_fast(unsigned sh, unsigned w
 
 // Word w (0..23) of a packed-BGR tile row from its 32 BGRX accumulator words: bytes 4w..4w+3 of the row
 // start in pixel w + w/3 at byte phase w % 3.
+__host__ __device__ __forceinline__ void tile_word_src(int w, int& p, unsigned& sel) {   // pixel pair p, p+1 and the PRMT selector
+  p = w + w / 3;
+  const int ph = w - (w / 3) * 3;
+  sel = ph == 0 ? 0x4210u : (ph == 1 ? 0x5421u : 0x6542u);
+}
 __host__ __device__ __forceinline__ unsigned tile_row_word(const unsigned* acc_row, int w) {
-  const int p = w + w / 3, ph = w - (w / 3) * 3;
-  const unsigned sel = ph == 0 ? 0x4210u : (ph == 1 ? 0x5421u : 0x6542u);
+  int p; unsigned sel;
+  tile_word_src(w, p, sel);
   return lane_perm(acc_row[p], acc_row[p + 1], sel);
 }
+// Interior write-out of k_bev_tma, who stores what: warp `wrp` owns tile rows wrp, wrp+8, wrp+16, wrp+24 (the rows it
+// accumulates with lanes along canvas x); lane l < 24 stores word l of each of them.
+__host__ __device__ __forceinline__ int tile_out_row32(int wrp, int i) { return wrp + 8 * i; }                 // i = 0..3
 
 // Slow path (kept out of line so the hot loop stays inside the instruction cache): entries with
 // out-of-frame taps (BORDER_CONSTANT 0 per tap; also every entry when the pitch is not a multiple

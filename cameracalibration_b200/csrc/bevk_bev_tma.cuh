@@ -576,10 +576,10 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
       // interior tile: warp w stores rows w, w+8, w+16, w+24, lanes 0..23 one packed-BGR word each (bytes 4l..4l+3 of a
       // row start in BGRX word l + l/3 at byte phase l % 3): four 96-byte row pieces per frame-set and warp
       if (lane < 24) {
-        const int wq = lane / 3, wph = lane - 3 * wq;
-        const unsigned wsel = wph == 0 ? 0x4210u : (wph == 1 ? 0x5421u : 0x6542u);
-        const unsigned wacc = acc_u32 + 4u * (unsigned)(wrp * ACC_WPITCH + lane + wq);
-        const int gy0 = tile.y + wrp;
+        int wp; unsigned wsel;
+        tile_word_src(lane, wp, wsel);
+        const int gy0 = tile.y + tile_out_row32(wrp, 0);
+        const unsigned wacc = acc_u32 + 4u * (unsigned)(tile_out_row32(wrp, 0) * ACC_WPITCH + wp);
         const int rows = max(0, min(4, (P.oy1 - gy0 + 7) / 8));
         const size_t off = (size_t)(gy0 - P.oy) * P.out_pitch + (size_t)(tile.x - P.ox) * 3 + (size_t)lane * 4;
         if (P.car) tile_rows_out<NB, SCATTER, true, false>(P, wacc, wsel, off, rows, b0, nb, none);

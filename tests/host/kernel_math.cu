@@ -576,16 +576,42 @@ int main(int argc, char** argv) {
             lane_perm(a[2], a[3], 0x6542) == want[2], "4-pixel write-out chunk=%d", chunk);
     }
   }
-  // ---- coalesced write-out index map (k_bev_tma's interior tiles): 3 x 256 threads cover 32 rows x 24 words exactly once
-  {
-    int seen[TILE][24] = {};
-    for (int i = 0; i < 3; ++i)
-      for (int t = 0; t < 256; ++t) {
-        const int idx = i * 256 + t, r = idx / 24, w = idx - r * 24;
-        CHECK(r < TILE && w < 24, "index map out of range");
-        seen[r][w]++;
+  // ---- interior write-out of k_bev_tma (bevk_bev_tma.cuh): who stores what.  The lane map -- warp w, lane l < 24 -> word l
+  //      of rows w + 8i -- must cover the 32 rows x 24 words of a tile exactly once, stay inside the warp's own rows (the
+  //      rows it accumulates with lanes along canvas x: barrier-free units rely on it) and deliver the dense BGR bytes
+  for (int rep = 0; rep < 50; ++rep) {
+    unsigned acc[TILE][TILE + 1];
+    uint8_t dense[TILE][TILE * 3];
+    for (int r = 0; r < TILE; ++r) {
+      for (int p = 0; p < TILE; ++p) {
+        acc[r][p] = rnd() & 0x00ffffffu;
+        dense[r][3 * p] = acc[r][p] & 255u; dense[r][3 * p + 1] = (acc[r][p] >> 8) & 255u; dense[r][3 * p + 2] = (acc[r][p] >> 16) & 255u;
       }
-    for (int r = 0; r < TILE; ++r) for (int w = 0; w < 24; ++w) CHECK(seen[r][w] == 1, "word (%d,%d) written %d times", r, w, seen[r][w]);
+      acc[r][TILE] = 0xdeadbeefu;
+    }
+    for (int form = 0; form < 1; ++form) {
+      int seen[TILE][24] = {};
+      uint8_t out[TILE][TILE * 3];
+      memset(out, 0xEE, sizeof out);
+      for (int wrp = 0; wrp < 8; ++wrp)
+        for (int lane = 0; lane < 24; ++lane)
+          for (int i = 0; i < (form ? 2 : 4); ++i) {
+            const int row = tile_out_row32(wrp, i);
+            CHECK(row >= 0 && row < TILE && (row & 7) == wrp, "write-out row %d is not warp %d's", row, wrp);
+            for (int q = 0; q < (form ? 2 : 1); ++q) {
+              const int w = form ? 2 * (lane % 12) + q : lane;
+              int p; unsigned sel;
+              tile_word_src(w, p, sel);
+              CHECK(p + 1 <= TILE, "pixel pair of word %d", w);
+              const unsigned v = lane_perm(acc[row][p], acc[row][p + 1], sel);
+              memcpy(out[row] + 4 * w, &v, 4);
+              seen[row][w]++;
+            }
+          }
+      for (int r = 0; r < TILE; ++r)
+        for (int w = 0; w < 24; ++w) CHECK(seen[r][w] == 1, "form %d: word (%d,%d) written %d times", form, r, w, seen[r][w]);
+      CHECK(memcmp(out, dense, sizeof out) == 0, "form %d: write-out bytes", form);
+    }
   }
   printf("kernel_math: %lld interp cases, fails=%d\n", n_interp, fails);
   return fails ? 1 : 0;

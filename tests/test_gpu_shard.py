@@ -73,6 +73,37 @@ def test_camera_sharding_on_one_gpu_every_world_size(fx, blend):
         ShardedBev(e, "cameras", rank=0, world=2, connect=False).render(d_all, out, car)
 
 
+def test_peer_store_kernel_variant_on_one_gpu(fx):
+    """bevk_bev_run_scattered with a world of one: the render kernel's peer-store instantiation (k_bev_tma<.., SCATTER>)
+    writes the slabs through the peer table -- here its own receive buffer -- and the rank composes them; no second GPU
+    and no NCCL are needed for that.  Batch 6 (ragged tail of the 4-frame-set units), with and without the car."""
+    import ctypes as C
+    import torch
+    from cameracalibration_b200 import _lib as L
+    g = fx.geometry()
+    e, _ = _engine(fx, g, True, calib=fx.calib)
+    dev = torch.device("cuda", e.ctx.device)
+    F = fx.frames()
+    sets = [[np.ascontiguousarray(np.roll(f, 17 * i + 3 * c, axis=1)) for c, f in enumerate(F)] for i in range(6)]
+    d_all = torch.from_numpy(np.stack([np.stack(s) for s in sets])).to(dev)
+    car = torch.from_numpy(fx.car()).to(dev)
+    lib, h = e.ctx.lib, e.ctx.h
+    L.check(lib.bevk_shard_configure(h, L.SHARD_CAMERAS, 0, 1))
+    handle = (C.c_uint8 * 64)()
+    L.check(lib.bevk_shard_prepare(h, 6, handle))
+    L.check(lib.bevk_shard_attach(h, bytes(handle)))
+    for c in (None, car):
+        full = torch.empty((6, g.BH, g.BW, 3), dtype=torch.uint8, device=dev)
+        e.run_stack(d_all.data_ptr(), g.FH * g.FW * 3, 6, full.data_ptr(), 0 if c is None else c.data_ptr())
+        own = torch.zeros((6, g.BH, g.BW, 3), dtype=torch.uint8, device=dev)
+        n_own = C.c_int()
+        L.check(lib.bevk_bev_run_scattered(h, C.c_void_p(d_all.data_ptr()), g.FH * g.FW * 3, 6, C.c_void_p(0 if c is None else c.data_ptr()), 0,
+                                           C.c_void_p(own.data_ptr()), C.byref(n_own)))
+        e.ctx.sync()
+        assert n_own.value == 6 and e.last_path() == "tma"
+        assert (own.cpu().numpy() == full.cpu().numpy()).all()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
