@@ -586,6 +586,9 @@ __global__ void __launch_bounds__(TMA_THREADS, MINCTAS) k_bev_tma(const TmaParam
         else if (rows == 4 && nb == NB && !none) tile_rows_out<NB, SCATTER, false, true>(P, wacc, wsel, off, rows, b0, nb, none);
         else tile_rows_out<NB, SCATTER, false, false>(P, wacc, wsel, off, rows, b0, nb, none);
       }
+      // the next unit may start without a CTA barrier (D_SYNC rules): lanes 24..31, which store nothing here, must not run
+      // ahead and overwrite accumulator words that lanes 0..23 of this warp are still reading
+      __syncwarp();
 #ifdef BEVK_TRACE
       if (tr) T[10] = clock64();
 #endif
