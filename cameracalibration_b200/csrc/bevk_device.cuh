@@ -234,15 +234,16 @@ __host__ __device__ __forceinline__ void hsv_roundtrip(int& b, int& g, int& r, i
   const float t1 = fmul(vf, fsub(1.0f, sf));
   const float t2 = fmul(vf, ffma(-sf, f, 1.0f));
   const float t3 = fmul(vf, ffma(-sf, fsub(1.0f, f), 1.0f));
-  float fb, fg, fr;
-  switch (sec) {   // sector table {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0}
-    case 0: fb = t1; fg = t3; fr = t0; break;
-    case 1: fb = t1; fg = t0; fr = t2; break;
-    case 2: fb = t3; fg = t0; fr = t1; break;
-    case 3: fb = t0; fg = t2; fr = t1; break;
-    case 4: fb = t0; fg = t1; fr = t3; break;
-    default: fb = t2; fg = t1; fr = t0; break;
-  }
+  // sector table {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0} (b, g, r pick t[.]), anything else like sector 5 --
+  // as selects, not as a switch: neighbouring pixels lie in different sectors, and a six-way divergent branch per pixel was
+  // what k_lum_spans spent its time on.  Two bits per sector and channel:
+  const unsigned sc = (unsigned)sec > 5u ? 10u : 2u * (unsigned)sec;
+  const unsigned ib = ((1u | 1u << 2 | 3u << 4 | 0u << 6 | 0u << 8 | 2u << 10) >> sc) & 3u;
+  const unsigned ig = ((3u | 0u << 2 | 0u << 4 | 2u << 6 | 1u << 8 | 1u << 10) >> sc) & 3u;
+  const unsigned ir = ((0u | 2u << 2 | 1u << 4 | 1u << 6 | 3u << 8 | 0u << 10) >> sc) & 3u;
+  float fb = (ib & 2u) ? ((ib & 1u) ? t3 : t2) : ((ib & 1u) ? t1 : t0);
+  float fg = (ig & 2u) ? ((ig & 1u) ? t3 : t2) : ((ig & 1u) ? t1 : t0);
+  float fr = (ir & 2u) ? ((ir & 1u) ? t3 : t2) : ((ir & 1u) ? t1 : t0);
   fb = fmul(fb, 255.0f); fg = fmul(fg, 255.0f); fr = fmul(fr, 255.0f);
   if (rounding_tail) {   // the < 32-pixel row tail goes through OpenCV's scalar path, which rounds
     b = max(0, min(255, f2i_rn(fb)));

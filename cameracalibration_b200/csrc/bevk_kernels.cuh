@@ -457,45 +457,65 @@ __global__ void __launch_bounds__(256) k_lum_apply(const uint8_t* const* __restr
 // is not converted (about 17 % of a frame at the fixture geometry, 4.6x fewer HSV round trips
 // than converting the four taps of every output pixel).  grid = (FH, n_frames).
 // ---------------------------------------------------------------------------------
-constexpr int LUM_ROWS = 1;   // source rows per CTA (8 measured 6 % slower than 1: the kernel is latency-, not prologue-bound)
+constexpr int LUM_ROWS = 16;   // source rows per CTA
 
+// One CTA converts the sampled spans of LUM_ROWS consecutive source rows of one frame.  The work items -- groups of 4
+// pixels = 3 aligned words in, 3 out -- of all its rows form ONE flat list (prefix sums of the rows' group counts in shared
+// memory) that the threads stride through, so that a row with a short span costs nothing and every thread has several
+// independent groups in flight.  Measured (cfg3, 32 x 4 frames at 1080p, profiles/r02_launches_summary.txt): a CTA per row
+// 0.235 ms, this form 0.235 ms, with the branch-free sector selection of hsv_roundtrip 0.211 ms; staging 32-group chunks
+// through shared memory for coalesced loads and stores was slower again (0.232 ms).
 __global__ void __launch_bounds__(128) k_lum_spans(const uint8_t* const* __restrict__ frames, uint8_t* const* __restrict__ outs,
                                                    const int2* __restrict__ spans, int n_cam, int w, int h,
                                                    const int* __restrict__ delta, const int* __restrict__ hsv_tab) {
-  const int f = blockIdx.y, y0 = blockIdx.x * LUM_ROWS, y1 = min(h, y0 + LUM_ROWS);
+  const int f = blockIdx.y, y0 = blockIdx.x * LUM_ROWS, y1 = min(h, y0 + LUM_ROWS), nrows = y1 - y0;
   const int2* sp_cam = spans + (size_t)(f % n_cam) * h;
-  bool any = false;
-  for (int y = y0; y < y1; ++y) any |= sp_cam[y].y > sp_cam[y].x;
-  if (!any) return;
   __shared__ int s_tab[512];
+  __shared__ int s_pref[LUM_ROWS + 1], s_g0[LUM_ROWS];
+  const bool words = (w & 3) == 0 && ((reinterpret_cast<uintptr_t>(frames[f]) | reinterpret_cast<uintptr_t>(outs[f])) & 3) == 0;
+  if (threadIdx.x == 0) {
+    // groups cover each span rounded out to multiples of 4 pixels: the extra pixels are converted too, which nobody samples
+    int acc = 0;
+    for (int r = 0; r < nrows; ++r) {
+      const int2 sp = sp_cam[y0 + r];
+      const int g0 = sp.x >> 2, g1 = sp.y > sp.x ? (sp.y + 3) >> 2 : g0;
+      s_pref[r] = acc; s_g0[r] = g0;
+      acc += g1 - g0;
+    }
+    for (int r = nrows; r <= LUM_ROWS; ++r) s_pref[r] = acc;
+  }
   for (int i = threadIdx.x; i < 512; i += 128) s_tab[i] = hsv_tab[i];
   __syncthreads();
+  const int total = s_pref[LUM_ROWS];
+  if (total == 0) return;
   const int d = delta[f], tail = w - (w % 32);
-  const bool words = (w & 3) == 0 && ((reinterpret_cast<uintptr_t>(frames[f]) | reinterpret_cast<uintptr_t>(outs[f])) & 3) == 0;
-  for (int y = y0; y < y1; ++y) {
-    const int2 sp = sp_cam[y];
-    if (sp.y <= sp.x) continue;
-    const uint8_t* src = frames[f] + (size_t)y * w * 3;
-    uint8_t* dst = outs[f] + (size_t)y * w * 3;
-    if (words) {
-      // groups of 4 pixels = 3 aligned words in, 3 out (rows start on a word boundary when w % 4 == 0).  The groups cover
-      // the span rounded out to multiples of 4: the extra pixels are converted too, which nobody samples.
-      const int g0 = sp.x >> 2, g1 = (sp.y + 3) >> 2;
-      for (int gidx = g0 + threadIdx.x; gidx < g1; gidx += 128) {
-        const unsigned* q = reinterpret_cast<const unsigned*>(src) + 3 * gidx;
-        const unsigned w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);       // B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
-        int c[12];
+  if (words) {
+    const size_t row_words = (size_t)w * 3 / 4;
+    const unsigned* src0 = reinterpret_cast<const unsigned*>(frames[f]) + (size_t)y0 * row_words;
+    unsigned* dst0 = reinterpret_cast<unsigned*>(outs[f]) + (size_t)y0 * row_words;
+    int r = 0;
+#pragma unroll 2
+    for (int i = threadIdx.x; i < total; i += 128) {
+      while (i >= s_pref[r + 1]) ++r;                       // the thread's items are visited in increasing order
+      const int gidx = s_g0[r] + (i - s_pref[r]);
+      const unsigned* q = src0 + (size_t)r * row_words + 3 * gidx;
+      const unsigned w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);       // B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+      int c[12];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { c[i] = (w0 >> (8 * i)) & 255; c[4 + i] = (w1 >> (8 * i)) & 255; c[8 + i] = (w2 >> (8 * i)) & 255; }
-        const bool rt = 4 * gidx >= tail;      // tail is a multiple of 4 here: a group is entirely body or entirely row tail
+      for (int k = 0; k < 4; ++k) { c[k] = (w0 >> (8 * k)) & 255; c[4 + k] = (w1 >> (8 * k)) & 255; c[8 + k] = (w2 >> (8 * k)) & 255; }
+      const bool rt = 4 * gidx >= tail;      // tail is a multiple of 4 here: a group is entirely body or entirely row tail
 #pragma unroll
-        for (int px = 0; px < 4; ++px) hsv_roundtrip(c[3 * px], c[3 * px + 1], c[3 * px + 2], d, rt, s_tab, s_tab + 256);
-        unsigned* o = reinterpret_cast<unsigned*>(dst) + 3 * gidx;
-        o[0] = (unsigned)c[0] | ((unsigned)c[1] << 8) | ((unsigned)c[2] << 16) | ((unsigned)c[3] << 24);
-        o[1] = (unsigned)c[4] | ((unsigned)c[5] << 8) | ((unsigned)c[6] << 16) | ((unsigned)c[7] << 24);
-        o[2] = (unsigned)c[8] | ((unsigned)c[9] << 8) | ((unsigned)c[10] << 16) | ((unsigned)c[11] << 24);
-      }
-    } else {
+      for (int px = 0; px < 4; ++px) hsv_roundtrip(c[3 * px], c[3 * px + 1], c[3 * px + 2], d, rt, s_tab, s_tab + 256);
+      unsigned* o = dst0 + (size_t)r * row_words + 3 * gidx;
+      o[0] = (unsigned)c[0] | ((unsigned)c[1] << 8) | ((unsigned)c[2] << 16) | ((unsigned)c[3] << 24);
+      o[1] = (unsigned)c[4] | ((unsigned)c[5] << 8) | ((unsigned)c[6] << 16) | ((unsigned)c[7] << 24);
+      o[2] = (unsigned)c[8] | ((unsigned)c[9] << 8) | ((unsigned)c[10] << 16) | ((unsigned)c[11] << 24);
+    }
+  } else {
+    for (int y = y0; y < y1; ++y) {
+      const int2 sp = sp_cam[y];
+      const uint8_t* src = frames[f] + (size_t)y * w * 3;
+      uint8_t* dst = outs[f] + (size_t)y * w * 3;
       for (int x = sp.x + threadIdx.x; x < sp.y; x += 128) {
         int b = src[3 * x], g = src[3 * x + 1], r = src[3 * x + 2];
         hsv_roundtrip(b, g, r, d, x >= tail, s_tab, s_tab + 256);
